@@ -1,0 +1,224 @@
+"""Generates tests/golden/*.npz by running the REFERENCE's own Python, imported
+unchanged from /root/reference, on seeded inputs (CPU).
+
+Run in the build container only (the reference checkout does not travel):
+    python tests/golden/make_golden.py
+What is the reference's own arithmetic (decoder, rendering, losses, samplers,
+RandomOptimizer, Mesher weight blend) is pinned by these vectors.  The tcnn
+encodings are not available offline, so inside JointEncoding they are supplied
+by oracle/shims/tinycudann (= the oracle): fixtures that depend on them pin the
+reference's *composition* of the encodings, not tcnn itself (parity unpinned).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = os.environ.get("MIPSFUSION_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
+sys.path.insert(0, REF)
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+np.bool = bool                                                   # numpy>=1.24 dropped the alias the reference uses
+torch.Tensor.cuda = lambda self, *a, **k: self                   # model/decoder.py:29 on a CPU box
+
+from helper_functions import sampling_helper as ref_samp        # noqa: E402
+from helper_functions import utils as ref_utils                 # noqa: E402
+from model.decoder import MLP_reg                                # noqa: E402
+from model.scene_rep import JointEncoding                        # noqa: E402
+from RandomOptimizer import RandomOptimizer                      # noqa: E402
+from vis import math_helper as ref_mh                            # noqa: E402
+
+from oracle import scene as oscene                               # noqa: E402
+
+
+def small_config(hash_size=10):
+    cfg = oscene.default_config()
+    cfg["grid"]["hash_size"] = hash_size
+    cfg["tracking"] = {"RO": {"particle_size": 48, "initial_scaling_factor": 0.02, "rescaling_factor": 0.5,
+                              "n_rows": 6, "n_cols": 8}, "ignore_edge_W": 2, "ignore_edge_H": 2}
+    return cfg
+
+
+def gen_lattice():
+    out = {}
+    for k, a in enumerate([(460, 620, 16, 24), (460, 620, 150, 200), (460, 620, 24, 32), (460, 620, 15, 20),
+                           (480, 640, 16, 24), (60, 80, 6, 8), (7, 9, 7, 9)]):
+        r, c = ref_samp.sample_pixels_uniformly(*a)
+        out[f"args{k}"] = np.asarray(a); out[f"rows{k}"] = r.numpy(); out[f"cols{k}"] = c.numpy()
+    np.savez_compressed(os.path.join(OUT, "lattice.npz"), **out)
+
+
+def gen_sampling():
+    g = torch.Generator().manual_seed(11)
+    H, W = 60, 80
+    depth = torch.rand(H, W, generator=g) * 3
+    depth[torch.rand(H, W, generator=g) < 0.1] = 0.0
+    keys_n = torch.randn(H * W, generator=g)                     # the randn draw; reference takes abs()
+    out = {"depth": depth.numpy(), "keys": keys_n.abs().numpy()}
+    orig = torch.randn_like
+    torch.randn_like = lambda t, *a, **k: keys_n.reshape(t.shape).clone()
+    try:
+        out["valid_random_200"] = ref_samp.sample_valid_pixels_random(depth, 200).numpy()
+        r, c = ref_samp.sample_pixels_mix(H, W, 6, 8, depth, 300)
+        out["mix_rows"], out["mix_cols"] = r.numpy(), c.numpy()
+    finally:
+        torch.randn_like = orig
+    idx = torch.arange(0, H * W, 7)
+    r, c = ref_samp.pixel_indices_to_rc(idx, H, W)
+    out["rc_idx"], out["rc_rows"], out["rc_cols"] = idx.numpy(), r.numpy(), c.numpy()
+    np.savez_compressed(os.path.join(OUT, "sampling.npz"), **out)
+
+
+def gen_losses():
+    g = torch.Generator().manual_seed(5)
+    R, S = 32, 75
+    z = torch.sort(torch.rand(R, S, generator=g) * 5, -1)[0]
+    d = torch.rand(R, 1, generator=g) * 4 + 0.3
+    d[:4] = 0.0
+    sdf = torch.rand(R, S, generator=g) * 2 - 1
+    prob = torch.softmax(torch.randn(R, S, 5, generator=g), -1)
+    out = {"z": z.numpy(), "d": d.numpy(), "sdf": sdf.numpy(), "prob": prob.numpy()}
+    for tag, emd in (("emd", 0.01), ("noemd", 0.0)):
+        fs, sl = ref_utils.get_sdf_loss(z, d, sdf, prob, 0.1, 5, emd, "l2")
+        out[f"fs_{tag}"], out[f"sdf_{tag}"] = fs.numpy(), sl.numpy()
+    fm, sm, fw, sw = ref_utils.get_masks(z, d, 0.1)
+    out["front_mask"], out["sdf_mask"] = fm.numpy(), sm.numpy()
+    out["fs_weight"], out["sdf_weight"] = np.float32(fw), np.float32(sw)
+    out["counts"] = np.asarray([int(torch.count_nonzero(fm)), int(torch.count_nonzero(sm))])
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), **out)
+
+
+def gen_decoder():
+    torch.manual_seed(0)
+    dec = MLP_reg(None, input_ch=32, input_ch_pos=48)
+    g = torch.Generator().manual_seed(3)
+    N = 96
+    embed = (torch.rand(N, 32, generator=g) * 2 - 1) * 0.3
+    pts = torch.rand(N, 3, generator=g)
+    embed_pos = torch.sin(torch.rand(N, 48, generator=g) * 6.0)
+    out = dec(embed, embed_pos, pts)
+    fx = {"embed": embed.numpy(), "embed_pos": embed_pos.numpy(), "pts": pts.numpy(), "out": out.detach().numpy()}
+    for k, v in dec.state_dict().items():
+        fx["w:" + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "decoder.npz"), **fx)
+
+
+def build_ref_model(cfg):
+    bb = torch.from_numpy(np.array(cfg["mapping"]["bound"]))                 # fp64, mipsfusion.py:94
+    nf = torch.from_numpy(np.array(cfg["mapping"]["localMLP_max_len"]))
+    torch.manual_seed(0)
+    model = JointEncoding(cfg, bb, nf)
+    # make the MLP weights non-degenerate for the SDF head and give the grid visible amplitude
+    g = torch.Generator().manual_seed(21)
+    with torch.no_grad():
+        model.embed_fn.params.copy_((torch.rand(model.embed_fn.params.shape, generator=g) * 2 - 1) * 0.5)
+    return model
+
+
+def gen_scene():
+    from mipsfusion_b200 import synth
+    cfg = small_config(10)
+    model = build_ref_model(cfg)
+    model.train()
+    g = torch.Generator().manual_seed(9)
+    c2w = synth.trajectory(4)[1]
+    dirs = synth.camera_rays()
+    frame = synth.render_frame(c2w, dirs[::23, ::31].contiguous())           # 20 x 20 pixel sub-lattice
+    rays = synth.frame_rays(frame)
+    R = 40
+    sel = torch.randperm(rays.shape[0], generator=g)[:R]
+    rays = rays[sel]
+    rays[:3, 6] = 0.0                                                        # a few invalid-depth rays
+    rays_d = torch.sum(rays[:, None, :3] * c2w[None, :3, :3], -1)
+    rays_o = c2w[None, :3, 3].repeat(R, 1)
+    rays_o.requires_grad_(True); rays_d.requires_grad_(True)
+    S = cfg["training"]["n_samples_d"] + cfg["training"]["n_range_d"]
+    u = torch.rand(R, S, generator=g)
+    orig = torch.rand
+    torch.rand = lambda *a, **k: u.clone()                                   # scene_rep.py:176
+    try:
+        ret = model.forward(rays_o, rays_d, rays[:, 3:6], rays[:, 6:7])
+        rend = model.render_rays(rays_o.detach(), rays_d.detach(), target_d=rays[:, 6:7])
+    finally:
+        torch.rand = orig
+    t = cfg["training"]
+    loss = t["rgb_weight"] * ret["rgb_loss"] + t["sdf_weight"] * ret["sdf_loss"] + t["fs_weight"] * ret["fs_loss"]
+    loss.backward()
+    fx = {"c2w": c2w.numpy(), "rays": rays.numpy(), "rays_o": rays_o.detach().numpy(), "rays_d": rays_d.detach().numpy(),
+          "u": u.numpy(), "loss": loss.detach().numpy(), "z_vals": rend["z_vals"].numpy(), "raw": rend["raw"].detach().numpy(),
+          "rgb": ret["rgb"].detach().numpy(), "depth": ret["depth"].detach().numpy(),
+          "depth_var": rend["depth_var"].detach().numpy(), "acc_map": rend["acc_map"].detach().numpy(),
+          "disp_map": rend["disp_map"].detach().numpy(),
+          "g_rays_o": rays_o.grad.numpy(), "g_rays_d": rays_d.grad.numpy(), "hash_size": np.asarray(10)}
+    for k in ("rgb_loss", "depth_loss", "sdf_loss", "fs_loss", "psnr"):
+        fx[k] = ret[k].detach().numpy()
+    for k, v in model.state_dict().items():
+        fx["w:" + k] = v.numpy()
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            fx["g:" + k] = p.grad.numpy()
+    # points-only query (run_network) on scattered points incl. outside the bound
+    pts = (torch.rand(128, 3, generator=g) * torch.tensor([4.0, 7.0, 4.6]) + torch.tensor([-0.8, 0.3, -1.3]))
+    with torch.no_grad():
+        fx["q_pts"] = pts.numpy(); fx["q_out"] = model.run_network(pts).numpy()
+    np.savez_compressed(os.path.join(OUT, "scene.npz"), **fx)
+    return cfg, model
+
+
+def gen_ro(cfg, model):
+    H, W = 60, 80
+    g = torch.Generator().manual_seed(13)
+    fx_, cx_, cy_ = 40.0, 39.5, 29.5
+    i, j = torch.meshgrid(torch.arange(W, dtype=torch.float32), torch.arange(H, dtype=torch.float32), indexing="xy")
+    dirs = torch.stack([(i - cx_) / fx_, -(j - cy_) / fx_, -torch.ones_like(i)], -1)
+    from mipsfusion_b200 import synth
+    c2w = synth.trajectory(4)[2]
+    frame = synth.render_frame(c2w, dirs, invalid_frac=0.05, seed=3)
+    depth = frame["depth"]
+    ds = types.SimpleNamespace(H=H, W=W, fx=fx_, fy=fx_, cx=cx_, cy=cy_, rays_d=dirs)
+    slam = types.SimpleNamespace(dataset=ds, device="cpu")
+    np.random.seed(7)
+    ro = RandomOptimizer(cfg, slam)
+    model.eval()
+    init = c2w.clone()
+    init[:3, 3] += torch.tensor([0.02, -0.015, 0.01])
+    pose = ro.optimize(model, depth, init.clone(), c2w.clone(), n_iter=3)
+    # one scoring pass with the template at the initial search size (fitness is the kernel's output)
+    pst7 = ro.pose_6D_to_7D(ro.pre_sampled_particle * 0.02)
+    R_, t_ = ro.get_abs_pose(init[:3, :3], init[:3, 3:], pst7)
+    td = depth[ro.row_indices, ro.col_indices].unsqueeze(-1)
+    rd = dirs[ro.row_indices, ro.col_indices, :]
+    with torch.no_grad():
+        fit, msdf = ro.get_fitness(model, R_, t_, c2w, td, rd)
+    np.savez_compressed(os.path.join(OUT, "ro.npz"), depth=depth.numpy(), dirs=dirs.numpy(), c2w=c2w.numpy(),
+                        init=init.numpy(), particles=ro.pre_sampled_particle.numpy(), pose=pose.numpy(),
+                        rows=ro.row_indices.numpy(), cols=ro.col_indices.numpy(), fitness=fit.numpy(),
+                        mean_sdf=msdf.numpy(), abs_rot=R_.numpy(), abs_trans=t_.numpy())
+
+
+def gen_blend():
+    rng = np.random.RandomState(4)
+    G, M = 257, 4
+    ent = rng.rand(G, M).astype(np.float32) * 2
+    dw = rng.rand(G, M).astype(np.float32)
+    mask = rng.rand(G, M) < 0.5
+    mask[:5] = False
+    dist = rng.rand(300).astype(np.float32) * 3
+    np.savez_compressed(os.path.join(OUT, "blend.npz"), entropy=ent, dist_w=dw, mask=mask,
+                        weights=ref_mh.compute_weights(ent, dw, mask), dist=dist,
+                        dist_weight=ref_mh.convert_dist_to_weight(dist))
+
+
+if __name__ == "__main__":
+    gen_lattice(); gen_sampling(); gen_losses(); gen_decoder()
+    cfg, model = gen_scene()
+    gen_ro(cfg, model)
+    gen_blend()
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(OUT, f)))
