@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the MIPSFusion per-frame neural-field hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Headline metric (BASELINE.json): map-step rays/s -- one mapping iteration = z-sampling, fused
+encode+MLP forward, SDF->weight render + losses, full backward, dense Adam -- on the BASELINE shape
+4096 rays x 43 samples, T = 2^19 hash grid, synthetic SDF-room frame.  The same JSON line also carries
+the tracking metric (pose candidates/s at 1024 x 2048) under "also".
+
+N > 1 (torchrun): data-parallel mapping, one 4096-ray batch per rank (weak scaling), global mask counts
+all-reduced before the loss and gradients all-reduced before Adam (NCCL).
+--impl reference: the CPU implementation of the same step (the oracle port of the reference's PyTorch
+path; the reference checkout itself does not travel to the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+R_RAYS, N_SAMPLES_D, N_RANGE_D, HASH = 4096, 32, 11, 19
+S = N_SAMPLES_D + N_RANGE_D
+ALG_BYTES_PER_POINT_BWD = 2048          # 1,024 B scatter (+ 1,024 B re-gather for the recomputed forward)
+ALG_BYTES_PER_POINT_FWD = 1024
+ADAM_BYTES_PER_PARAM = 32
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(parts[0])); mx = float(parts[1])
+            except Exception:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(seed):
+    import helpers as H
+    return H.synth_batch(R_RAYS, S, seed=seed, invalid=64)
+
+
+def build_model(seed=0):
+    import helpers as H
+    cfg = H.make_config(HASH, n_samples_d=N_SAMPLES_D, n_range_d=N_RANGE_D)
+    of = H.oracle_field(cfg, seed=seed)            # same init as the CPU arm: grid U(-1e-4,1e-4) seed 1337, nn.Linear default
+    return cfg, of
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_step_fn(n_rays, threads=None):
+    """The CPU arm: oracle port of JointEncoding.forward + loss.backward() + torch.optim.Adam.step()."""
+    import torch
+    from oracle import adam as oadam
+    torch.set_num_threads(threads or os.cpu_count())
+    cfg, of = build_model()
+    opt = oadam.make_optimizer(of)
+    rays_o, rays_d, rgb, d, u = make_inputs(0)
+    sl = slice(0, n_rays)
+    args = (rays_o[sl], rays_d[sl], rgb[sl], d[sl], u[sl])
+
+    def step():
+        opt.zero_grad()
+        ret = of.forward(*args)
+        loss = of.total_loss(ret)
+        loss.backward()
+        opt.step()
+        return float(loss)
+    return step
+
+
+def run_reference(args):
+    """`--impl reference`: CPU implementation on the host cores, bounded sample per step."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_rays = 1024
+    step = cpu_step_fn(n_rays)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = n_rays * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = f"{args.steps} steps x {n_rays} rays x {S} samples (1/{R_RAYS // n_rays} of the 4096-ray batch), full T=2^19 grid + dense Adam"
+    print(json.dumps({
+        "impl": "reference", "metric": "map_step_rays_per_s", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(n):
+    return {"workload": f"C1 mapping step: {R_RAYS} rays x {S} samples ({N_SAMPLES_D} uniform + {N_RANGE_D} around depth) per GPU, "
+                        f"HashGrid T=2^{HASH} (9,014,144 params) + MLP_reg (36,577), forward + backward + dense Adam, one synthetic "
+                        "SDF-room 640x480 frame (BASELINE.json configs[0] shape; configs[1] tracking shape reported under 'also')",
+            "rays_per_gpu": R_RAYS, "samples_per_ray": S, "hash_size": HASH, "parallelism": f"dp{n}" if n > 1 else "single",
+            "l2": "per-step working set (grid p,g,m,v = 144 MB) exceeds the 126 MB L2; L2 additionally flushed (256 MB write) between timed steps"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import helpers as H
+    import mipsfusion_b200 as mf
+    from mipsfusion_b200.mapper import FusedMapper
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    cfg, of = build_model()
+    model = H.cuda_model(cfg, H.state_of(of))
+    rays_o, rays_d, rgb, d, _ = make_inputs(rank)
+    host = torch.cat([rays_o, rays_d, rgb, d], -1).contiguous().pin_memory()        # (R, 10) pinned host batch
+    dv = host.to(dev)
+    ro, rd, tc, td = dv[:, 0:3].contiguous(), dv[:, 3:6].contiguous(), dv[:, 6:9].contiguous(), dv[:, 9].contiguous()
+    mapper = FusedMapper(model, group=group)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        mapper.step(ro, rd, tc, td)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region: exactly K steps, device time per step (events), L2 flushed between steps ----
+    mapper.launches = 0
+    evs = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        losses = mapper.step(ro, rd, tc, td)
+        b.record()
+        evs.append((a, b))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    launches = mapper.launches
+    t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t)
+    value = world * R_RAYS * args.steps / (dev_ms * 1e-3)
+
+    # ---- per-kernel timing of the dominant kernel (separate pass, events around each launch) ----
+    mapper.timing = {}
+    for _ in range(args.steps):
+        flush.zero_()
+        mapper.step(ro, rd, tc, td)
+    torch.cuda.synchronize()
+    phase_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in mapper.timing.items()}
+    mapper.timing = None
+
+    # ---- e2e: public drop-in API, host buffers, H2D of the batch + D2H of the loss every step ----
+    model2 = H.cuda_model(cfg, H.state_of(of))
+    opt = mf.create_map_optimizer(model2, cfg["mapping"]["lr_decoder"], cfg["mapping"]["lr_embed"])
+    tw = cfg["training"]
+
+    def e2e_step():
+        batch = host.to(dev, non_blocking=True)
+        ret = model2(batch[:, 0:3], batch[:, 3:6], batch[:, 6:9], batch[:, 9:10])
+        loss = tw["rgb_weight"] * ret["rgb_loss"] + tw["sdf_weight"] * ret["sdf_loss"] + tw["fs_weight"] * ret["fs_loss"]
+        loss.backward()
+        if world > 1:
+            import torch.distributed as dist
+            for p in model2.parameters():
+                if p.grad is not None and p.numel():
+                    dist.all_reduce(p.grad); p.grad.mul_(1.0 / world)
+        opt.step(zero_grad=True)
+        return float(loss)                                   # D2H read of the step's result
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_dt = time.perf_counter() - t0
+    te = torch.tensor([e2e_dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * R_RAYS * args.steps / float(te)
+
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- tracking metric (BASELINE configs[1] shape): RandomOptimizer scoring 1024 candidates x 2048 pixels ----
+    also = {}
+    if world == 1:
+        also = tracking_bench(model, cfg, dev)
+
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+    hbm, tf, which = peaks()
+    P = R_RAYS * S
+    bwd_ms = phase_ms.get("field_bwd", float("nan"))
+    achieved = ALG_BYTES_PER_POINT_BWD * P / (bwd_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "field_bwd_kernel (recompute-forward + decoder backward + grid scatter)",
+            "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+            "peak_source": which, "ms_per_launch": bwd_ms, "alg_bytes_per_launch": ALG_BYTES_PER_POINT_BWD * P,
+            "phase_ms": phase_ms,
+            "adam_gbs": ADAM_BYTES_PER_PARAM * (9014144 + 36577) / (phase_ms.get("adam", float("nan")) * 1e-3) / 1e9,
+            "fwd_gbs": ALG_BYTES_PER_POINT_FWD * P / (phase_ms.get("field_fwd", float("nan")) * 1e-3) / 1e9}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        n_rays, steps = R_RAYS, 3
+        step = cpu_step_fn(n_rays)
+        step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_rays * steps / dt, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{steps} steps x {n_rays} rays x {S} samples (the full batch), full T=2^19 grid + dense Adam, "
+                         f"oracle port of the reference's PyTorch path, torch {torch.__version__}"}
+    out = {"metric": "map_step_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+           "roofline": roof, "cpu_baseline": cpu,
+           "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": 4,
+                   "api": "JointEncoding.forward + loss.backward() + FusedAdam.step()"},
+           "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": t_wall, "also": also}
+    print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def tracking_bench(model, cfg, dev, iters=5):
+    """pose candidates/s of RandomOptimizer scoring at the BASELINE tracking shape."""
+    import types
+    import torch
+    import mipsfusion_b200 as mf
+    from mipsfusion_b200 import synth
+    from oracle import sampling as osamp
+    Cn, nr, nc = 1024, 32, 64
+    tcfg = dict(cfg)
+    tcfg["tracking"] = {"RO": {"particle_size": Cn, "initial_scaling_factor": 0.02, "rescaling_factor": 0.5, "n_rows": nr, "n_cols": nc},
+                        "ignore_edge_W": 20, "ignore_edge_H": 20}
+    dirs = synth.camera_rays()
+    c2w = synth.trajectory(4)[1]
+    rows, cols = osamp.sample_pixels_uniformly(460, 620, nr, nc)
+    sub = synth.render_frame(c2w, dirs[rows, cols][None].contiguous())
+    ds = types.SimpleNamespace(H=460, W=620, fx=320.0, fy=320.0, cx=309.5, cy=229.5, rays_d=dirs)
+    g = torch.Generator().manual_seed(0)
+    particles = torch.randn(Cn, 6, generator=g).clamp(-2, 2); particles[0] = 0
+    ro = mf.RandomOptimizer(tcfg, types.SimpleNamespace(dataset=ds, device=str(dev)), particles=particles)
+    model.eval()
+    target_d = sub["depth"].reshape(-1).to(dev); rays_d = dirs[rows, cols].contiguous().to(dev)
+    rot, trans = c2w[:3, :3].contiguous().to(dev), c2w[:3, 3].contiguous().to(dev)
+    search = torch.full((6,), 0.02, device=dev)
+    for _ in range(2):
+        ro.score(model, rot, trans, search, target_d, rays_d)
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(iters):
+        fit, ms, p7 = ro.score(model, rot, trans, search, target_d, rays_d)
+        ro.update(fit, ms, p7, rot.clone(), trans.clone(), search.clone())
+    b.record(); torch.cuda.synchronize()
+    ms_it = a.elapsed_time(b) / iters
+    model.train()
+    return {"tracking_pose_candidates_per_s": Cn / (ms_it * 1e-3), "tracking_ms_per_ro_iteration": ms_it,
+            "tracking_shape": f"{Cn} candidates x {nr * nc} pixels, SDF-only field query + per-candidate reduction + swarm update"}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_gpu(a)

@@ -1,0 +1,227 @@
+/* mipsfusion_b200 -- C ABI of the B200-native MIPSFusion per-frame neural-field hot path.
+ *
+ * This is the drop-in boundary.  The reference has no C ABI: its
+ * boundary is Python (tcnn.Encoding, MLP_reg, JointEncoding, RandomOptimizer,
+ * Mesher).  Each entry point below names the reference interface it replaces
+ * (file:line relative to the reference checkout); the Python host mirror in
+ * mipsfusion_b200/ binds them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors are dense row-major fp32 unless stated; sizes are element counts;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *     nothing synchronises the device;
+ *   - return value: 0 on success, negative on error (MF_ERR_*); the message is
+ *     retrievable with mf_last_error() (thread-local).  Nothing throws or aborts;
+ *   - no global mutable state besides a per-process cache of device attributes.
+ */
+#ifndef MIPSFUSION_B200_H
+#define MIPSFUSION_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MF_ABI_VERSION 1
+#define MF_MAX_LEVELS 16
+#define MF_MLP_PARAMS 36577          /* reference model/decoder.py:32-50 with input_ch=32, input_ch_pos=48 */
+#define MF_RAW_DIM 10                /* rgb_raw(3) sdf(1) entropy(1) prob(5), model/decoder.py:74 */
+
+#define MF_OK 0
+#define MF_ERR_INVALID (-1)
+#define MF_ERR_CUDA (-2)
+#define MF_ERR_UNSUPPORTED (-3)
+
+/* Per-level table of the multi-resolution hash grid (tinycudann 1.7 GridEncoding;
+ * reference model/encodings.py:11-26).  Host-side POD, filled by mf_hashgrid_meta. */
+typedef struct {
+    int32_t n_levels, n_features, log2_hashmap_size, base_resolution;
+    float scale[MF_MAX_LEVELS];
+    uint32_t resolution[MF_MAX_LEVELS];
+    uint32_t size[MF_MAX_LEVELS];          /* entries per level */
+    uint32_t offset[MF_MAX_LEVELS + 1];    /* entry offsets; offset[n_levels] = total entries */
+    uint32_t hashed[MF_MAX_LEVELS];        /* 1: coherent-prime hash, 0: dense stride index */
+} mf_grid_meta;
+
+/* One submap's neural field ("localMLP"): reference model/scene_rep.py:11-45.
+ * Coordinate normalisation (scene_rep.py:138-142) is x_n = ((double)x - norm_a) / norm_b
+ * / norm_factor, evaluated in fp64 and rounded to fp32 once, as in the reference.
+ *   use_bound_normalize: norm_a = bound_min, norm_b = bound_max - bound_min
+ *   otherwise:           norm_a = -L,        norm_b = 2 L          (L = localMLP_max_len) */
+typedef struct {
+    const float* grid;        /* embed_fn.params, flat fp32, n_params */
+    const float* mlp_prep;    /* kernel-layout weights written by mf_mlp_prepare */
+    double norm_a[3], norm_b[3];
+    double norm_factor;       /* training.norm_factor */
+    mf_grid_meta meta;
+} mf_field;
+
+/* Scalars of reference model/scene_rep.py:153-238 + helper_functions/utils.py. */
+typedef struct {
+    int32_t n_samples_d;      /* training.n_samples_d (uniform); or training.n_samples when target_d is NULL */
+    int32_t n_range_d;        /* training.n_range_d (around depth); 0 when target_d is NULL */
+    int32_t perturb;          /* training.perturb > 0 */
+    int32_t rgb_missing_nz;   /* training.rgb_missing != 0 */
+    double trunc;             /* training.trunc        (python floats are doubles; the kernels round */
+    double sc_factor;         /* data.sc_factor         them to fp32 exactly where torch would)      */
+    double depth_trunc;       /* cam.depth_trunc */
+    double emd_w;             /* EMD_w argument of JointEncoding.forward */
+} mf_render_cfg;
+
+const char* mf_last_error(void);
+int mf_abi_version(void);
+/* Number of SMs of the current device (grid sizing); <0 on error. */
+int mf_device_sm_count(void);
+
+/* ---- a1: hash-grid encoding (replaces tcnn.Encoding "HashGrid", model/encodings.py:14-25) ---- */
+int mf_hashgrid_meta(int log2_hashmap_size, int n_levels, int n_features, int base_resolution,
+                     double per_level_scale, mf_grid_meta* meta_host);
+/* x (N,3) in the unit cube (wraps outside) -> out (N, L*F).  idx_dump (N,L,8) uint32 optional (NULL). */
+int mf_hashgrid_fwd(const float* x, const float* grid, const mf_grid_meta* meta_host, float* out,
+                    uint32_t* idx_dump, int64_t N, void* stream);
+/* grad_grid += scatter(dL_dy); dL_dx (N,3) optional (NULL). */
+int mf_hashgrid_bwd(const float* x, const float* dL_dy, const float* grid, const mf_grid_meta* meta_host,
+                    float* grad_grid, float* dL_dx, int64_t N, void* stream);
+
+/* ---- a2: frequency encoding (replaces tcnn.Encoding "Frequency", model/encodings.py:31-38) ---- */
+int mf_freq_fwd(const float* x, float* out, int n_dims, int n_frequencies, int64_t N, void* stream);
+int mf_freq_bwd(const float* x, const float* dL_dy, float* dL_dx, int n_dims, int n_frequencies, int64_t N, void* stream);
+
+/* ---- a3: decoder MLP_reg (model/decoder.py:6-75) ---- */
+/* `mlp` is the flat concatenation of the state_dict tensors in order:
+ * pts_linear.0.{weight(128,51),bias} pts_linear.2.{(128,128),bias} rgb_linear.0.{(3,115),bias}
+ * sdf_linear.0.{(128,96),bias} sdf_linear.2.{(5,128),bias}  = MF_MLP_PARAMS floats.
+ * mf_mlp_prepare re-lays it out for the kernels into mlp_prep (mf_mlp_prep_size() floats). */
+int64_t mf_mlp_prep_size(void);
+int mf_mlp_prepare(const float* mlp, float* mlp_prep, void* stream);
+/* MLP_reg.forward(embed (N,32), embed_pos (N,48), query_pts (N,3)) -> out (N,10) */
+int mf_mlp_fwd(const float* embed, const float* embed_pos, const float* pts, const float* mlp_prep,
+               float* out, int64_t N, void* stream);
+/* grad_mlp (MF_MLP_PARAMS, same layout as `mlp`) += ...; d_embed/d_embed_pos/d_pts optional (NULL).
+ * workspace: mf_mlp_grad_workspace_size() floats of scratch (per-CTA partial sums). */
+int64_t mf_mlp_grad_workspace_size(void);
+int mf_mlp_bwd(const float* embed, const float* embed_pos, const float* pts, const float* mlp_prep,
+               const float* d_out, float* grad_mlp, float* d_embed, float* d_embed_pos, float* d_pts,
+               float* workspace, int64_t N, void* stream);
+
+/* ---- a4: fused field query (JointEncoding.run_network / query_*, model/scene_rep.py:106-146) ----
+ * pts (N,3) fp32 in the submap frame -> out (N,10).  normalize=0 skips the bound normalisation
+ * (query_color_sdf called directly on pre-normalised points, as model/Mesher.py:487 does). */
+int mf_field_query(const float* pts, const mf_field* field_host, int normalize, float* out, int64_t N, void* stream);
+/* backward of the above: grad_grid/grad_mlp accumulate; d_pts (N,3) optional. */
+int mf_field_query_bwd(const float* pts, const mf_field* field_host, int normalize, const float* d_out,
+                       float* grad_grid, float* grad_mlp, float* d_pts, float* workspace, int64_t N, void* stream);
+
+/* ---- a5: z sampling (JointEncoding.render_rays, model/scene_rep.py:157-176) ----
+ * target_d (R) or NULL; u (R,S) jitter in [0,1) (the reference's torch.rand) or NULL when perturb=0;
+ * lin_uniform (n_samples_d) = linspace(near, far, n_samples_d); lin_range (n_range_d) =
+ * linspace(-range_d, range_d, n_range_d); lin_fallback (n_range_d) = linspace(near, far, n_range_d).
+ * Writes z (R,S), S = n_samples_d + n_range_d, and the global mask counts
+ * counts[0] = #front samples, counts[1] = #sdf samples (helper_functions/utils.py:43-44; int64, zeroed here). */
+int mf_sample_z(const float* target_d, const float* u, const float* lin_uniform, const float* lin_range,
+                const float* lin_fallback, const mf_render_cfg* cfg_host, float* z, int64_t* counts,
+                int64_t R, void* stream);
+
+/* ---- a4+a12 fused: points on rays pts = o + d z, field query -> raw (R,S,10) ---- */
+int mf_field_query_rays(const float* rays_o, const float* rays_d, const float* z, const mf_field* field_host,
+                        float* raw, int64_t R, int S, void* stream);
+/* d_raw (R,S,10) -> grad_grid, grad_mlp (accumulate), d_rays_o / d_rays_d (R,3; optional, overwritten). */
+int mf_field_query_rays_bwd(const float* rays_o, const float* rays_d, const float* z, const mf_field* field_host,
+                            const float* d_raw, float* grad_grid, float* grad_mlp, float* d_rays_o, float* d_rays_d,
+                            float* workspace, int64_t R, int S, void* stream);
+
+/* ---- a6-a8: SDF->weights rendering + losses (scene_rep.py:58-103,190-238; helper_functions/utils.py:21-111) ----
+ * out_rgb (R,3), out_depth (R), out_aux (R,3) = depth_var, disp_map, acc_map (optional); out_weights (R,S) normalised
+ * sample weights (optional); inds (R) int32 first-sign-change index (optional);
+ * losses (8) = rgb_loss, depth_loss, sdf_loss, fs_loss, psnr, fs_weight, sdf_weight, n_valid.
+ * target_rgb/target_d NULL => render only (eval mode), losses untouched.  scratch: R*8 floats. */
+int mf_render_loss_fwd(const float* raw, const float* z, const float* target_rgb, const float* target_d,
+                       const int64_t* counts, const mf_render_cfg* cfg_host, float* out_rgb, float* out_depth,
+                       float* out_aux, float* out_weights, int32_t* inds, float* losses, float* scratch,
+                       int64_t R, int S, void* stream);
+/* g_losses (4) upstream grads of rgb/depth/sdf/fs loss (device); g_rgb (R,3) / g_depth (R) optional upstream
+ * grads of the rendered maps -> d_raw (R,S,10). */
+int mf_render_loss_bwd(const float* raw, const float* z, const float* target_rgb, const float* target_d,
+                       const int64_t* counts, const float* losses, const mf_render_cfg* cfg_host,
+                       const float* g_losses, const float* g_rgb, const float* g_depth, float* d_raw,
+                       int64_t R, int S, void* stream);
+
+/* ---- a10: dense Adam (torch.optim.Adam as configured at mipsfusion.py:580-584) ----
+ * step >= 1; zero_grad != 0 also clears g (the reference's zero_grad, mipsfusion.py:335). */
+int mf_adam_step(float* p, float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                 double eps, double weight_decay, int step, int zero_grad, void* stream);
+
+/* ---- a11: pixel samplers (helper_functions/sampling_helper.py:7-68), int64 outputs ---- */
+int mf_sample_pixels_uniform(int img_h, int img_w, int num_h, int num_w, int64_t* rows, int64_t* cols, void* stream);
+/* top-`num` of keys*mask(depth>0 [and not on the lattice]) by (value desc, index asc); keys (H*W) >= 0.
+ * lattice_h/w = 0 => sample_valid_pixels_random (indices only, rows/cols may be NULL);
+ * else sample_pixels_mix: rows/cols (num) = lattice then random.  workspace: mf_topk_workspace_size(H*W) bytes. */
+int64_t mf_topk_workspace_size(int64_t n);
+int mf_sample_pixels_topk(const float* depth, const float* keys, int img_h, int img_w, int lattice_h, int lattice_w,
+                          int num, int64_t* indices, int64_t* rows, int64_t* cols, void* workspace, void* stream);
+
+/* ---- a12: ray generation (mipsfusion.py:320-322; geometry_helper.py:107-123; datasets/utils.py:29) ----
+ * dirs_cam (R,3); poses (K,4,4) c2w; pose_idx (R) int64 or NULL (=> pose 0) -> rays_o, rays_d (R,3). */
+int mf_gen_rays(const float* dirs_cam, const float* poses, const int64_t* pose_idx, float* rays_o, float* rays_d,
+                int64_t R, int K, void* stream);
+/* d_poses (K,4,4) += backward of mf_gen_rays (rotation block and translation column). */
+int mf_gen_rays_bwd(const float* dirs_cam, const int64_t* pose_idx, const float* d_rays_o, const float* d_rays_d,
+                    float* d_poses, int64_t R, int K, void* stream);
+
+/* ---- a13: RandomOptimizer particle scoring (RandomOptimizer.py:54-73,81-85,113-131) ----
+ * particles6 (C_total,6) pre-sampled template; search_size (6), rot_cur (3,3), trans_cur (3) device;
+ * dirs_cam (P,3) and target_d (P) are the sampled pixels.  c_begin/c_count select this rank's candidate
+ * shard.  -> fitness (c_count), mean_sdf (c_count), pst7 (c_count,7) rescaled 7-D particles.
+ * scratch: c_count*(P+12) floats. */
+int mf_ro_score(const float* particles6, const float* search_size, const float* rot_cur, const float* trans_cur,
+                const float* dirs_cam, const float* target_d, const mf_field* field_host, double trunc,
+                double sdf_weight, int c_begin, int c_count, int P, float* fitness, float* mean_sdf, float* pst7,
+                float* scratch, void* stream);
+/* Steps 3-5 of RandomOptimizer.optimize (RandomOptimizer.py:202-224) on device, over all C candidates:
+ * better mask, fitness-weighted mean transform, pose update, search-size update (in place).
+ * better_mask (C) uint8; info (4) int32 = count_nonzero(better), success_flag, argmin(fitness), 0. */
+int mf_ro_update(const float* fitness, const float* mean_sdf, const float* pst7, int C, double rescale,
+                 float* rot_cur, float* trans_cur, float* search_size, uint8_t* better_mask, int32_t* info,
+                 void* stream);
+
+/* ---- a14: joint multi-submap query + blend (model/Mesher.py:464-528,606-663; vis/math_helper.py:58-96) ----
+ * Query points are either explicit (pts (G,3) fp64 world coordinates, as trimesh vertices) or a regular
+ * grid given by its per-axis coordinates (the np.linspace arrays of Mesher.get_grid_uniform, Mesher.py:43-55),
+ * generated on the fly with index = (iy*nx + ix)*nz + iz.  All pointers are device pointers.
+ * g_begin/g_count select a contiguous range of the point index space (slab sharding across GPUs);
+ * per-point outputs are indexed relative to g_begin. */
+typedef struct {
+    const double* pts;        /* NULL => regular grid */
+    const double* ax; const double* ay; const double* az;
+    int32_t nx, ny, nz;
+} mf_point_set;
+
+typedef struct {
+    mf_field field;
+    float w2l[12];            /* inverse(first_kf_pose)[:3,:4] row-major: world -> submap frame (geometry_helper.py:93-99) */
+    double aabb_min[3], aabb_max[3];   /* inclusive containment test on fp64 coordinates (Mesher.py:168-175) */
+    float centroid[3];
+} mf_submap;
+
+int64_t mf_joint_query_scratch_size(int64_t g_count);   /* bytes */
+/* Pass 1: max_dist[m] = max over contained points of |x - centroid_m| (fp32; atomic max, so shards
+ * can be combined with a max-reduction).  max_dist (M) must be zero-initialised by the caller. */
+int mf_joint_query_maxdist(const mf_point_set* ps_host, const mf_submap* submaps_host, int M, int64_t g_begin,
+                           int64_t g_count, float* max_dist, void* stream);
+/* Pass 2, for submaps [m_begin, m_begin+m_count): acc (g_count,K) += w * value and w, K = 2 (sdf) or 4 (rgb);
+ * w = exp(-10 clip(entropy,0,1e4)) * N(dist; 0, max_dist/3) for points inside the AABB (and vis != 0);
+ * mask_any (g_count) |= contained & visible; contain (g_count,M) uint8 optional; vis (g_count,M) uint8 optional. */
+int mf_joint_query_accumulate(const mf_point_set* ps_host, const mf_submap* submaps_host, int M, int m_begin,
+                              int m_count, const float* max_dist, const uint8_t* vis, int color, int64_t g_begin,
+                              int64_t g_count, float* acc, uint8_t* mask_any, uint8_t* contain, void* scratch,
+                              void* stream);
+/* Pass 3: out (g_count, K-1) = acc[:, :K-1] / acc[:, K-1] where mask_any (0 if the weight sum is 0), else the
+ * fill value (-1 for sdf, 0 for rgb)  (Mesher.py:461,525-527). */
+int mf_joint_query_finalize(const float* acc, const uint8_t* mask_any, int color, int64_t g_count, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIPSFUSION_B200_H */

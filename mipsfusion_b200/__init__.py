@@ -1,0 +1,15 @@
+"""mipsfusion_b200: B200-native (sm_100a CUDA) implementation of MIPSFusion's per-frame neural-field
+hot path behind the reference's Python call surface.
+
+    from mipsfusion_b200 import JointEncoding, get_encoder, MLP_reg, RandomOptimizer
+
+The compute lives in ``libmipsfusion_b200.so`` (C ABI, include/mipsfusion_b200.h); importing this
+package does not load it, the first kernel call does -- and raises if it has not been built."""
+from ._lib import MipsFusionB200Error, lib, load_library  # noqa: F401
+from .encodings import get_encoder, HashGridEncoding, FrequencyEncoding, IdentityEncoding  # noqa: F401
+from .decoder import MLP_reg  # noqa: F401
+from .scene_rep import JointEncoding  # noqa: F401
+from .optim import FusedAdam, create_map_optimizer  # noqa: F401
+from .random_optimizer import RandomOptimizer  # noqa: F401
+from .joint_query import JointSubmapQuery, get_grid_uniform  # noqa: F401
+from . import sampling_helper  # noqa: F401

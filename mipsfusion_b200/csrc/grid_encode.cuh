@@ -1,0 +1,133 @@
+// Multi-resolution hash grid: index arithmetic, gather, scatter and input gradient.
+// Restates the published algorithm of tinycudann 1.7 (encodings/grid.h) that the reference
+// selects at model/encodings.py:14-25 -- see oracle/hashgrid.py for the normative definition.
+#pragma once
+#include "mf_common.cuh"
+
+constexpr uint32_t MF_PRIME1 = 2654435761u;
+constexpr uint32_t MF_PRIME2 = 805459861u;
+
+struct LevelInfo {
+    float scale;
+    uint32_t res, size, offset, hashed;
+};
+
+__device__ __forceinline__ LevelInfo level_info(const FieldDev& f, int l) {
+    LevelInfo li;
+    li.scale = f.scale[l]; li.res = f.res[l]; li.size = f.size[l]; li.offset = f.offset[l]; li.hashed = f.hashed[l];
+    return li;
+}
+
+// grid_index<3, CoherentPrime>: all arithmetic is uint32 with wrap-around.
+__device__ __forceinline__ uint32_t grid_index(uint32_t px, uint32_t py, uint32_t pz, const LevelInfo& li) {
+    uint32_t idx;
+    if (li.hashed) {
+        idx = px ^ (py * MF_PRIME1) ^ (pz * MF_PRIME2);
+    } else {
+        idx = px + py * li.res + pz * (li.res * li.res);
+    }
+    if (idx >= li.size) idx %= li.size;
+    return idx;
+}
+
+// pos_fract(): pos = fmaf(scale, x, 0.5); cell = (uint32)(int)floor(pos); frac = pos - floor(pos)
+__device__ __forceinline__ void pos_fract(float x, float scale, uint32_t& cell, float& frac) {
+    float pos = fmaf(scale, x, 0.5f);
+    float fl = floorf(pos);
+    cell = (uint32_t)(int)fl;
+    frac = pos - fl;
+}
+
+__device__ __forceinline__ float corner_weight(int c, const float f[3]) {
+    float w = 1.0f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) w = __fmul_rn(w, ((c >> d) & 1) ? f[d] : __fsub_rn(1.0f, f[d]));
+    return w;
+}
+
+// Forward gather of one level: 8 corners, 2 features.  idx_out (8) optional.
+__device__ __forceinline__ float2 grid_level_fwd(const float x[3], const float2* __restrict__ grid2,
+                                                 const LevelInfo& li, uint32_t* idx_out) {
+    uint32_t g[3]; float f[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) pos_fract(x[d], li.scale, g[d], f[d]);
+    uint32_t idx[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        idx[c] = grid_index(g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + ((c >> 2) & 1), li);
+    float2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = __ldg(&grid2[li.offset + idx[c]]);     // 8 independent gathers in flight
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float w = corner_weight(c, f);
+        acc.x = fmaf(w, v[c].x, acc.x);
+        acc.y = fmaf(w, v[c].y, acc.y);
+        if (idx_out) idx_out[c] = idx[c];
+    }
+    return acc;
+}
+
+__device__ __forceinline__ void red_add_f2(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+// Backward of one level: scatter w * dy into grad (kernel_grid_backward) and, if WANT_DX,
+// return dL/dx contribution (kernel_grid_backward_input; needs the forward features).
+template <bool WANT_DX>
+__device__ __forceinline__ void grid_level_bwd(const float x[3], float2 dy, const float2* __restrict__ grid2,
+                                               float* __restrict__ grad, const LevelInfo& li, float dx[3]) {
+    uint32_t g[3]; float f[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) pos_fract(x[d], li.scale, g[d], f[d]);
+    uint32_t idx[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        idx[c] = grid_index(g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + ((c >> 2) & 1), li);
+    if (dy.x != 0.f || dy.y != 0.f) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float w = corner_weight(c, f);
+            red_add_f2(grad + 2 * (size_t)(li.offset + idx[c]), w * dy.x, w * dy.y);
+        }
+    }
+    if (WANT_DX) {
+        float2 v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = __ldg(&grid2[li.offset + idx[c]]);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            // d/dx_d of the trilinear blend: scale * sum over the 4 corner pairs along d
+            const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+            float s = 0.f;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    float w = (a ? f[d1] : 1.0f - f[d1]) * (b ? f[d2] : 1.0f - f[d2]);
+                    int c0 = (a << d1) | (b << d2);
+                    int c1 = c0 | (1 << d);
+                    s += w * ((v[c1].x - v[c0].x) * dy.x + (v[c1].y - v[c0].y) * dy.y);
+                }
+            dx[d] += li.scale * s;
+        }
+    }
+}
+
+// Coordinate normalisation of JointEncoding.run_network (model/scene_rep.py:138-142) followed by
+// "/ norm_factor" (:119): fp64 arithmetic, one rounding to fp32 (the bound tensors are float64).
+__device__ __forceinline__ void normalize_point(const FieldDev& f, const float p[3], float x[3]) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x[d] = (float)((((double)p[d] - f.na[d]) / f.nb[d]) / f.nf);
+}
+__device__ __forceinline__ void prenormalized_point(const FieldDev& f, const float p[3], float x[3]) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x[d] = (f.nf == 1.0) ? p[d] : __fdiv_rn(p[d], (float)f.nf);   // fp32 tensor / python scalar
+}
+
+// Frequency encoding argument: fl(fl(x * 2^k) * PI) (+ fl(PI/2)); oracle/frequency.py.
+__device__ __forceinline__ float freq_arg(float x, int k, int s) {
+    float a = __fmul_rn(ldexpf(x, k), 3.14159274101257324f);
+    return s ? __fadd_rn(a, 1.57079637050628662f) : a;
+}

@@ -1,0 +1,263 @@
+// Dense Adam (a10) and the integer-exact pixel samplers (a11).
+// Reference: mipsfusion.py:580-584 (torch.optim.Adam configuration), torch's single-tensor Adam op order;
+// helper_functions/sampling_helper.py:7-68.
+#include "mf_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// Adam.  One pass over (p, g, m, v): 16 B read + 12 B write (+4 B when the gradient is cleared)
+// per parameter -- a pure HBM stream.
+// ---------------------------------------------------------------------------------------------
+struct AdamScalars {
+    float w1;          // fp32(1 - beta1): lerp weight
+    float beta2, w2;   // fp32(beta2), fp32(1 - beta2)
+    float neg_step;    // fp32(-lr / (1 - beta1^t))
+    float bc2_sqrt;    // fp32(sqrt(1 - beta2^t))
+    float eps, wd;
+};
+
+__device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, const AdamScalars& a) {
+    float gg = g;
+    if (a.wd != 0.f) gg = fmaf(a.wd, p, gg);                        // grad.add(param, alpha=wd)
+    m = fmaf(gg - m, a.w1, m);                                      // exp_avg.lerp_(grad, 1 - beta1)
+    v = fmaf(a.w2 * gg, gg, v * a.beta2);                           // mul_(beta2).addcmul_(g, g, 1 - beta2)
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), a.bc2_sqrt), a.eps);
+    p = fmaf(a.neg_step, __fdiv_rn(m, denom), p);                   // addcdiv_(m, denom, value=-step_size)
+}
+
+template <bool ZERO>
+__global__ void __launch_bounds__(256) adam_kernel_v4(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
+                                                      float4* __restrict__ v, int64_t n4, AdamScalars a) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+        adam_one(pp.x, gg.x, mm.x, vv.x, a); adam_one(pp.y, gg.y, mm.y, vv.y, a);
+        adam_one(pp.z, gg.z, mm.z, vv.z, a); adam_one(pp.w, gg.w, mm.w, vv.w, a);
+        p[i] = pp; m[i] = mm; v[i] = vv;
+        if (ZERO) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <bool ZERO>
+__global__ void adam_kernel_scalar(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                   int64_t begin, int64_t n, AdamScalars a) {
+    const int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+    adam_one(pp, gg, mm, vv, a);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+    if (ZERO) g[i] = 0.f;
+}
+
+MF_API int mf_adam_step(float* p, float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
+                        double weight_decay, int step, int zero_grad, void* stream) {
+    MF_CHECK_ARG(n >= 0 && step >= 1);
+    if (n == 0) return MF_OK;
+    MF_CHECK_ARG(p && g && m && v);
+    AdamScalars a;
+    a.w1 = (float)(1.0 - beta1); a.beta2 = (float)beta2; a.w2 = (float)(1.0 - beta2);
+    a.neg_step = (float)(-(lr / (1.0 - pow(beta1, (double)step))));
+    a.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
+    a.eps = (float)eps; a.wd = (float)weight_decay;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool aligned = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
+    const int64_t n4 = aligned ? n / 4 : 0;
+    if (n4 > 0) {
+        const int64_t want = (n4 + 255) / 256;
+        const int64_t cap = (int64_t)mf_sm_count_cached() * 8;
+        const unsigned blocks = (unsigned)(want < cap ? want : cap);
+        if (zero_grad) adam_kernel_v4<true><<<blocks, 256, 0, st>>>((float4*)p, (float4*)g, (float4*)m, (float4*)v, n4, a);
+        else adam_kernel_v4<false><<<blocks, 256, 0, st>>>((float4*)p, (float4*)g, (float4*)m, (float4*)v, n4, a);
+        MF_LAUNCH_CHECK();
+    }
+    const int64_t rest = n - n4 * 4;
+    if (rest > 0) {
+        const unsigned blocks = (unsigned)((rest + 255) / 256);
+        if (zero_grad) adam_kernel_scalar<true><<<blocks, 256, 0, st>>>(p, g, m, v, n4 * 4, n, a);
+        else adam_kernel_scalar<false><<<blocks, 256, 0, st>>>(p, g, m, v, n4 * 4, n, a);
+        MF_LAUNCH_CHECK();
+    }
+    return MF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Uniform lattice (sampling_helper.py:38-48).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline void lattice_params(int len, int num, int& step, int& start) {
+    const int interval = (len - num) / (num + 1), offset = (len - num) % (num + 1);
+    step = interval + 1; start = interval + offset / 2;
+}
+
+__global__ void lattice_kernel(int img_h, int img_w, int num_h, int num_w, int64_t* __restrict__ rows, int64_t* __restrict__ cols) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_h * num_w) return;
+    int sh, oh, sw, ow;
+    lattice_params(img_h, num_h, sh, oh);
+    lattice_params(img_w, num_w, sw, ow);
+    rows[t] = (int64_t)(t / num_w) * sh + oh;
+    cols[t] = (int64_t)(t % num_w) * sw + ow;
+}
+
+MF_API int mf_sample_pixels_uniform(int img_h, int img_w, int num_h, int num_w, int64_t* rows, int64_t* cols, void* stream) {
+    MF_CHECK_ARG(img_h > 0 && img_w > 0 && num_h > 0 && num_w > 0 && num_h <= img_h && num_w <= img_w && rows && cols);
+    lattice_kernel<<<(num_h * num_w + 255) / 256, 256, 0, (cudaStream_t)stream>>>(img_h, img_w, num_h, num_w, rows, cols);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Top-k of keys*mask by (value descending, index ascending): torch.topk(samp_v, num)[1] with the
+// tie rule made explicit (oracle/sampling.py).  Every element gets the distinct 64-bit key
+//   key = (float_bits(v) << 32) | ~index        (v >= 0, so the bit pattern is order preserving)
+// and the k largest keys are found by an MSB-first radix select (6 digit passes, each pass one
+// kernel whose last-finishing block scans the histogram), then compacted and sorted by one CTA.
+// ---------------------------------------------------------------------------------------------
+constexpr int TOPK_MAX = 4096;
+constexpr int RADIX_BINS = 2048;
+
+struct TopkState {
+    unsigned long long prefix;      // digits fixed so far (aligned to their bit position)
+    unsigned long long mask;        // which bits of the key are fixed
+    int k_rem;                      // how many keys are still to be taken at / below the prefix
+    unsigned int done;              // block ticket of the current pass
+    unsigned int n_sel;             // compaction cursor
+    unsigned int hist[RADIX_BINS];
+};
+
+__device__ __forceinline__ unsigned long long topk_key(const float* __restrict__ depth, const float* __restrict__ keys,
+                                                       int64_t i, int img_w, int lat_h, int lat_w, int sh, int oh, int sw, int ow) {
+    float mask = depth[i] > 0.f ? 1.f : 0.f;
+    if (lat_h > 0) {                                   // sample_pixels_mix: lattice pixels are excluded (:58)
+        const int r = (int)(i / img_w), c = (int)(i % img_w);
+        const int rr = r - oh, cc = c - ow;
+        if (rr >= 0 && cc >= 0 && rr % sh == 0 && cc % sw == 0 && rr / sh < lat_h && cc / sw < lat_w) mask = 0.f;
+    }
+    const float v = __fmul_rn(mask, keys[i]);
+    return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(~(unsigned int)i);
+}
+
+__global__ void topk_init_kernel(TopkState* st, int k) {
+    const int t = threadIdx.x + blockIdx.x * blockDim.x;
+    if (t == 0) { st->prefix = 0ull; st->mask = 0ull; st->k_rem = k; st->done = 0u; st->n_sel = 0u; }
+    if (t < RADIX_BINS) st->hist[t] = 0u;
+}
+
+__global__ void __launch_bounds__(256) topk_pass_kernel(const float* __restrict__ depth, const float* __restrict__ keys, int64_t n,
+                                                        int img_w, int lat_h, int lat_w, int sh, int oh, int sw, int ow,
+                                                        int shift, int bits, TopkState* st) {
+    __shared__ unsigned int h[RADIX_BINS];
+    __shared__ bool last;
+    const int nb = 1 << bits;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) h[b] = 0u;
+    __syncthreads();
+    const unsigned long long prefix = st->prefix, mask = st->mask;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = topk_key(depth, keys, i, img_w, lat_h, lat_w, sh, oh, sw, ow);
+        if ((key & mask) == prefix) atomicAdd(&h[(unsigned int)(key >> shift) & (nb - 1)], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x)
+        if (h[b]) atomicAdd(&st->hist[b], h[b]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(&st->done, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // the last block: walk the histogram from the top digit down (single thread; <= 2048 bins)
+    if (threadIdx.x == 0) {
+        int k = st->k_rem, b = nb - 1;
+        volatile unsigned int* gh = st->hist;
+        for (; b > 0; --b) {
+            const int c = (int)gh[b];
+            if (c >= k) break;
+            k -= c;
+        }
+        st->k_rem = k;
+        st->prefix = prefix | ((unsigned long long)b << shift);
+        st->mask = mask | ((unsigned long long)(nb - 1) << shift);
+        st->done = 0u;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) st->hist[b] = 0u;
+}
+
+__global__ void __launch_bounds__(256) topk_compact_kernel(const float* __restrict__ depth, const float* __restrict__ keys, int64_t n,
+                                                           int img_w, int lat_h, int lat_w, int sh, int oh, int sw, int ow,
+                                                           TopkState* st, unsigned long long* __restrict__ sel, int k) {
+    const unsigned long long thr = st->prefix;        // after the last pass: the k-th largest key itself
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = topk_key(depth, keys, i, img_w, lat_h, lat_w, sh, oh, sw, ow);
+        if (key >= thr) {
+            const unsigned int slot = atomicAdd(&st->n_sel, 1u);
+            if (slot < (unsigned int)k) sel[slot] = key;
+        }
+    }
+}
+
+// One CTA: bitonic sort (descending) of the k selected keys, then decode the indices.
+__global__ void __launch_bounds__(1024) topk_sort_kernel(const unsigned long long* __restrict__ sel, int k, int img_w,
+                                                         int n_lat, int64_t* __restrict__ indices, int64_t* __restrict__ rows,
+                                                         int64_t* __restrict__ cols) {
+    __shared__ unsigned long long s[TOPK_MAX];
+    int np2 = 1;
+    while (np2 < k) np2 <<= 1;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) s[i] = i < k ? sel[i] : 0ull;
+    __syncthreads();
+    for (int size = 2; size <= np2; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const bool desc = (i & size) == 0;
+                    const unsigned long long a = s[i], b = s[j];
+                    if (desc ? (a < b) : (a > b)) { s[i] = b; s[j] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const int64_t idx = (int64_t)(~(unsigned int)(s[i] & 0xffffffffull));
+        if (indices) indices[i] = idx;
+        if (rows) { rows[n_lat + i] = idx / img_w; cols[n_lat + i] = idx % img_w; }
+    }
+}
+
+MF_API int64_t mf_topk_workspace_size(int64_t n) { (void)n; return (int64_t)sizeof(TopkState) + TOPK_MAX * sizeof(unsigned long long) + 256; }
+
+MF_API int mf_sample_pixels_topk(const float* depth, const float* keys, int img_h, int img_w, int lattice_h, int lattice_w, int num,
+                                 int64_t* indices, int64_t* rows, int64_t* cols, void* workspace, void* stream) {
+    MF_CHECK_ARG(depth && keys && workspace && img_h > 0 && img_w > 0);
+    MF_CHECK_ARG((lattice_h > 0) == (lattice_w > 0));
+    MF_CHECK_ARG((rows == nullptr) == (cols == nullptr));
+    const int n_lat = lattice_h * lattice_w;
+    const int k = num - n_lat;
+    const int64_t n = (int64_t)img_h * img_w;
+    MF_CHECK_ARG(k >= 0 && k <= TOPK_MAX && k <= n);
+    MF_CHECK_ARG(n < (1ll << 32));
+    MF_CHECK_ARG(lattice_h == 0 || (rows && lattice_h <= img_h && lattice_w <= img_w));
+    MF_CHECK_ARG(indices || rows);
+    cudaStream_t st = (cudaStream_t)stream;
+    int sh = 1, oh = 0, sw = 1, ow = 0;
+    if (n_lat > 0) {
+        lattice_params(img_h, lattice_h, sh, oh);
+        lattice_params(img_w, lattice_w, sw, ow);
+        lattice_kernel<<<(n_lat + 255) / 256, 256, 0, st>>>(img_h, img_w, lattice_h, lattice_w, rows, cols);
+        MF_LAUNCH_CHECK();
+    }
+    if (k == 0) return MF_OK;
+    TopkState* state = (TopkState*)workspace;
+    unsigned long long* sel = (unsigned long long*)((char*)workspace + ((sizeof(TopkState) + 255) / 256) * 256);
+    topk_init_kernel<<<(RADIX_BINS + 255) / 256, 256, 0, st>>>(state, k);
+    MF_LAUNCH_CHECK();
+    const int64_t want = (n + 255) / 256;
+    const unsigned blocks = (unsigned)(want < 2 * mf_sm_count_cached() ? want : 2 * mf_sm_count_cached());
+    const int shifts[6] = {53, 42, 32, 21, 10, 0}, nbits[6] = {11, 11, 10, 11, 11, 10};
+    for (int p = 0; p < 6; ++p) {
+        topk_pass_kernel<<<blocks, 256, 0, st>>>(depth, keys, n, img_w, lattice_h, lattice_w, sh, oh, sw, ow, shifts[p], nbits[p], state);
+        MF_LAUNCH_CHECK();
+    }
+    topk_compact_kernel<<<blocks, 256, 0, st>>>(depth, keys, n, img_w, lattice_h, lattice_w, sh, oh, sw, ow, state, sel, k);
+    MF_LAUNCH_CHECK();
+    topk_sort_kernel<<<1, 1024, 0, st>>>(sel, k, img_w, n_lat, indices, rows, cols);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}

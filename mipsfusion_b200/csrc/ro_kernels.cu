@@ -1,0 +1,202 @@
+// RandomOptimizer: particle pose-candidate scoring and the swarm update (a13).
+// Reference: RandomOptimizer.py:54-73 (6D->7D, absolute poses), :81-85,113-131 (fitness), :202-224 (update).
+#include "field_launch.cuh"
+
+// pytorch3d.transforms.quaternion_to_matrix (real part first, two_s = 2 / |q|^2)
+__device__ __forceinline__ void quat_to_mat(const float q[4], float m[9]) {
+    const float r = q[0], i = q[1], j = q[2], k = q[3];
+    const float two_s = 2.0f / (((r * r + i * i) + j * j) + k * k);
+    m[0] = 1 - two_s * (j * j + k * k); m[1] = two_s * (i * j - k * r); m[2] = two_s * (i * k + j * r);
+    m[3] = two_s * (i * j + k * r); m[4] = 1 - two_s * (i * i + k * k); m[5] = two_s * (j * k - i * r);
+    m[6] = two_s * (i * k - j * r); m[7] = two_s * (j * k + i * r); m[8] = 1 - two_s * (i * i + j * j);
+}
+
+__device__ __forceinline__ void mat3_mul(const float a[9], const float b[9], float c[9]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int col = 0; col < 3; ++col)
+            c[r * 3 + col] = fmaf(a[r * 3 + 2], b[6 + col], fmaf(a[r * 3 + 1], b[3 + col], a[r * 3] * b[col]));
+}
+
+// per candidate: rescaled particle -> 7-D pose -> absolute rotation / translation
+__global__ void ro_pose_kernel(const float* __restrict__ particles6, const float* __restrict__ search_size,
+                               const float* __restrict__ rot_cur, const float* __restrict__ trans_cur, int c_begin, int c_count,
+                               float* __restrict__ Rt, float* __restrict__ pst7) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c_count) return;
+    float p[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) p[k] = __fmul_rn(particles6[(size_t)(c_begin + c) * 6 + k], search_size[k]);
+    const float imag = __fadd_rn(__fadd_rn(__fmul_rn(p[0], p[0]), __fmul_rn(p[1], p[1])), __fmul_rn(p[2], p[2]));
+    const float qw = imag <= 1.0f ? sqrtf(1.0f - imag) : 0.0f;               // pose_6D_to_7D
+    const float q[4] = {qw, p[0], p[1], p[2]};
+    float dR[9], R0[9], R[9];
+    quat_to_mat(q, dR);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R0[k] = rot_cur[k];
+    mat3_mul(R0, dR, R);                                                      // get_abs_pose
+    float* o = Rt + (size_t)c * 12;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) o[k] = R[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o[9 + k] = trans_cur[k] + p[3 + k];
+    float* s = pst7 + (size_t)c * 7;
+    s[0] = qw;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s[1 + k] = p[k];
+}
+
+struct SrcRO {                             // world point of (candidate, pixel): R_c (d_cam * depth) + t_c
+    const float* Rt; const float* dirs; const float* depth; int P;
+    __device__ __forceinline__ void point(int64_t i, const FieldDev& f, float x[3]) const {
+        const int64_t c = i / P; const int p = (int)(i % P);
+        const float dp = depth[p];
+        const float cam[3] = {__fmul_rn(dirs[p * 3], dp), __fmul_rn(dirs[p * 3 + 1], dp), __fmul_rn(dirs[p * 3 + 2], dp)};
+        const float* R = Rt + c * 12;
+        float w[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            w[j] = __fadd_rn(fmaf(R[j * 3 + 2], cam[2], fmaf(R[j * 3 + 1], cam[1], __fmul_rn(R[j * 3], cam[0]))), R[9 + j]);
+        normalize_point(f, w, x);
+    }
+};
+
+struct EpiAbsSdf {                         // valid * |sdf * trunc| per (candidate, pixel)
+    float* out; const float* depth; int P; float trunc;
+    __device__ __forceinline__ void store(const float* sm, int64_t tile, int64_t N) const {
+        const int m = threadIdx.x;
+        const int64_t i = tile * TP + m;
+        if (m < TP && i < N) {
+            const float valid = depth[i % P] > 0.f ? 1.f : 0.f;
+            out[i] = valid * fabsf(__fmul_rn(sm[(ROW_OUT + 3) * LDA + m], trunc));
+        }
+    }
+};
+
+// mean over the pixels of one candidate (warp per candidate; fixed summation order)
+__global__ void ro_reduce_kernel(const float* __restrict__ vals, int c_count, int P, float sdf_weight,
+                                 float* __restrict__ fitness, float* __restrict__ mean_sdf) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= c_count) return;
+    float s = 0.f;
+    for (int p = lane; p < P; p += 32) s += vals[(size_t)c * P + p];
+    s = warp_sum(s);
+    if (lane == 0) {
+        const float mean = s / (float)P;
+        mean_sdf[c] = mean;
+        fitness[c] = mean * sdf_weight;
+    }
+}
+
+// Swarm update (single CTA): RandomOptimizer.py:202-224
+__global__ void __launch_bounds__(1024) ro_update_kernel(const float* __restrict__ fitness, const float* __restrict__ mean_sdf,
+                                                         const float* __restrict__ pst7, int C, float rescale,
+                                                         float* __restrict__ rot_cur, float* __restrict__ trans_cur,
+                                                         float* __restrict__ search_size, uint8_t* __restrict__ better_mask,
+                                                         int32_t* __restrict__ info) {
+    __shared__ double red[32][9];
+    __shared__ int red_cnt[32], red_arg[32];
+    __shared__ float red_min[32];
+    const float f0 = fitness[0];
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};       // sum w, sum w*mean_sdf, sum w*pst7[0..6]
+    int cnt = 0, arg = 0x7fffffff; float fmin_ = INFINITY;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float f = fitness[c];
+        const bool better = f < f0;
+        if (better_mask) better_mask[c] = better ? 1 : 0;
+        if (f < fmin_) { fmin_ = f; arg = c; }
+        if (better) {
+            const float w = f0 - f;
+            cnt += 1;
+            acc[0] += (double)w;
+            acc[1] += (double)(w * mean_sdf[c]);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) acc[2 + k] += (double)(pst7[(size_t)c * 7 + k] * w);
+        }
+    }
+    const int w_ = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = warp_sum_d(acc[k]);
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        const float of = __shfl_xor_sync(0xffffffffu, fmin_, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (of < fmin_ || (of == fmin_ && oa < arg)) { fmin_ = of; arg = oa; }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) red[w_][k] = acc[k];
+        red_cnt[w_] = cnt; red_arg[w_] = arg; red_min[w_] = fmin_;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    double t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int count = 0, amin = 0x7fffffff; float vmin = INFINITY;
+    const int nw = blockDim.x >> 5;
+    for (int i = 0; i < nw; ++i) {
+        for (int k = 0; k < 9; ++k) t[k] += red[i][k];
+        count += red_cnt[i];
+        if (red_min[i] < vmin || (red_min[i] == vmin && red_arg[i] < amin)) { vmin = red_min[i]; amin = red_arg[i]; }
+    }
+    const bool success = count > 0;
+    const float wsum = (float)t[0] + 0.00001f;
+    float mean_s, mt6[6];
+    if (success) {
+        mean_s = (float)t[1] / wsum;
+        float mt[7];
+        for (int k = 0; k < 7; ++k) mt[k] = (float)t[2 + k] / wsum;
+        const float nrm = sqrtf(((mt[0] * mt[0] + mt[1] * mt[1]) + mt[2] * mt[2]) + mt[3] * mt[3]) + 1e-5f;
+        float q[4];
+        for (int k = 0; k < 4; ++k) q[k] = mt[k] / nrm;
+        float dR[9], R0[9], R[9];
+        quat_to_mat(q, dR);
+        for (int k = 0; k < 9; ++k) R0[k] = rot_cur[k];
+        mat3_mul(R0, dR, R);                                           // update_cur_pose
+        for (int k = 0; k < 9; ++k) rot_cur[k] = R[k];
+        for (int k = 0; k < 3; ++k) trans_cur[k] += mt[4 + k];
+        mt6[0] = q[1]; mt6[1] = q[2]; mt6[2] = q[3]; mt6[3] = mt[4]; mt6[4] = mt[5]; mt6[5] = mt[6];
+    } else {
+        mean_s = mean_sdf[0];
+        for (int k = 0; k < 6; ++k) mt6[k] = 0.f;                      // no_rel_trans[1:]
+    }
+    float s[6], n2 = 0.f;
+    for (int k = 0; k < 6; ++k) { s[k] = fabsf(mt6[k]) + 0.0001f; n2 += s[k] * s[k]; }
+    const float nrm = sqrtf(n2);
+    for (int k = 0; k < 6; ++k) {
+        const float ss = rescale * mean_s * s[k] / nrm + 0.0001f;      // update_search_size
+        search_size[k] = success ? ss : ss * 2.0f;
+    }
+    if (info) { info[0] = count; info[1] = success ? 1 : 0; info[2] = amin; info[3] = 0; }
+}
+
+MF_API int mf_ro_score(const float* particles6, const float* search_size, const float* rot_cur, const float* trans_cur,
+                       const float* dirs_cam, const float* target_d, const mf_field* field, double trunc, double sdf_weight,
+                       int c_begin, int c_count, int P, float* fitness, float* mean_sdf, float* pst7, float* scratch, void* stream) {
+    MF_CHECK_ARG(c_begin >= 0 && c_count >= 0 && P > 0);
+    if (c_count == 0) return MF_OK;
+    MF_CHECK_ARG(particles6 && search_size && rot_cur && trans_cur && dirs_cam && target_d && fitness && mean_sdf && pst7 && scratch);
+    FieldDev d; int rc = mf_field_to_dev(field, &d); if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* Rt = scratch;                                   // c_count * 12
+    float* vals = scratch + (size_t)c_count * 12;          // c_count * P
+    ro_pose_kernel<<<(c_count + 127) / 128, 128, 0, st>>>(particles6, search_size, rot_cur, trans_cur, c_begin, c_count, Rt, pst7);
+    MF_LAUNCH_CHECK();
+    SrcRO src{Rt, dirs_cam, target_d, P};
+    EpiAbsSdf epi{vals, target_d, P, (float)trunc};
+    rc = launch_field_fwd<SrcRO, EpiAbsSdf, true>(d, src, epi, (int64_t)c_count * P, st);
+    if (rc) return rc;
+    ro_reduce_kernel<<<(c_count + 7) / 8, 256, 0, st>>>(vals, c_count, P, (float)sdf_weight, fitness, mean_sdf);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}
+
+MF_API int mf_ro_update(const float* fitness, const float* mean_sdf, const float* pst7, int C, double rescale, float* rot_cur,
+                        float* trans_cur, float* search_size, uint8_t* better_mask, int32_t* info, void* stream) {
+    MF_CHECK_ARG(C > 0 && fitness && mean_sdf && pst7 && rot_cur && trans_cur && search_size);
+    ro_update_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(fitness, mean_sdf, pst7, C, (float)rescale, rot_cur, trans_cur,
+                                                           search_size, better_mask, info);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}

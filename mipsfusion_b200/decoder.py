@@ -1,0 +1,111 @@
+"""Drop-in for reference model/decoder.py: ``MLP_reg`` with the same constructor, parameter names
+(state_dict keys) and ``forward(embed, embed_pos, query_pts) -> (N, 10)``, evaluated by the fused
+decoder kernels (mf_mlp_fwd / mf_mlp_bwd)."""
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+PARAM_ORDER = ["pts_linear.0.weight", "pts_linear.0.bias", "pts_linear.2.weight", "pts_linear.2.bias",
+               "rgb_linear.0.weight", "rgb_linear.0.bias", "sdf_linear.0.weight", "sdf_linear.0.bias",
+               "sdf_linear.2.weight", "sdf_linear.2.bias"]
+
+
+class _Workspace:
+    """Per-device scratch for the per-CTA partial parameter gradients (never pickled)."""
+    _bufs = {}
+
+    @classmethod
+    def get(cls, device, extra_floats=0):
+        n = int(L.lib().mf_mlp_grad_workspace_size()) + int(extra_floats)
+        key = (device.type, device.index)
+        buf = cls._bufs.get(key)
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(n, device=device, dtype=torch.float32)
+            cls._bufs[key] = buf
+        return buf
+
+
+class _MLPFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, embed, embed_pos, pts, prep, *params):
+        N = embed.shape[0]
+        out = torch.empty(N, L.MF_RAW_DIM, device=embed.device, dtype=torch.float32)
+        L.call("mf_mlp_fwd", L.ptr(embed), L.ptr(embed_pos), L.ptr(pts), L.ptr(prep), L.ptr(out), N, L.stream())
+        ctx.save_for_backward(embed, embed_pos, pts, prep)
+        ctx.shapes = [p.shape for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        embed, embed_pos, pts, prep = ctx.saved_tensors
+        N = embed.shape[0]
+        dev = embed.device
+        g_mlp = torch.zeros(L.MF_MLP_PARAMS, device=dev, dtype=torch.float32)
+        d_embed = torch.empty_like(embed) if ctx.needs_input_grad[0] else None
+        want_dx = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        d_pos = torch.empty_like(embed_pos) if want_dx else None
+        d_pts = torch.empty_like(pts) if want_dx else None
+        L.call("mf_mlp_bwd", L.ptr(embed), L.ptr(embed_pos), L.ptr(pts), L.ptr(prep), L.ptr(d_out.contiguous()), L.ptr(g_mlp),
+               L.ptr(d_embed), L.ptr(d_pos), L.ptr(d_pts), L.ptr(_Workspace.get(dev)), N, L.stream())
+        grads, o = [], 0
+        for shp in ctx.shapes:
+            n = shp.numel()
+            grads.append(g_mlp[o:o + n].view(shp))
+            o += n
+        return (d_embed, d_pos if ctx.needs_input_grad[1] else None, d_pts if ctx.needs_input_grad[2] else None, None, *grads)
+
+
+class MLP_reg(nn.Module):
+    """MLP with SDF classification head -- reference model/decoder.py:6-75."""
+
+    def __init__(self, cfg, input_ch=3, input_ch_pos=12, n_hidden=128, n_hidden_rgb=64, n_hidden_sdf=64,
+                 n_hidden_branch=128, n_class=5, beta=80.):
+        super().__init__()
+        self.cfg = cfg
+        self.input_ch = input_ch
+        self.input_ch_pos = input_ch_pos + 3
+        self.n_hidden, self.n_hidden_rgb, self.n_hidden_sdf, self.n_hidden_branch = n_hidden, n_hidden_rgb, n_hidden_sdf, n_hidden_branch
+        self.n_class, self.max_class_Id, self.beta = n_class, n_class - 1, beta
+        if (self.input_ch, self.input_ch_pos, n_hidden, n_hidden_rgb, n_hidden_sdf, n_hidden_branch, n_class) != (32, 51, 128, 64, 64, 128, 5):
+            raise L.MipsFusionB200Error(
+                "MLP_reg kernels are built for the reference instantiation (input_ch=32, input_ch_pos=48, widths "
+                "128/64/64/128, 5 classes; model/scene_rep.py:45); got a different shape")
+        self.pts_linear = nn.Sequential(nn.Linear(self.input_ch_pos, n_hidden), nn.ReLU(), nn.Linear(n_hidden, n_hidden_sdf + n_hidden_rgb))
+        self.rgb_linear = nn.Sequential(nn.Linear(n_hidden_rgb + self.input_ch_pos, 3))
+        self.sdf_linear = nn.Sequential(nn.Linear(n_hidden_sdf + self.input_ch, n_hidden_branch), nn.ReLU(),
+                                        nn.Linear(n_hidden_branch, n_class), nn.Softmax(dim=-1))
+
+    def ordered_params(self):
+        sd = dict(self.named_parameters())
+        return [sd[k] for k in PARAM_ORDER]
+
+    def flat_weights(self):
+        """The state_dict tensors concatenated in order (MF_MLP_PARAMS floats)."""
+        return torch.cat([p.detach().reshape(-1) for p in self.ordered_params()])
+
+    def prepared(self):
+        """Kernel-layout weights, rebuilt only when a parameter changed (mf_mlp_prepare)."""
+        ps = self.ordered_params()
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        cache = self.__dict__.get("_prep_cache")
+        if cache is None or cache[0] != key:
+            dev = ps[0].device
+            if dev.type != "cuda":
+                raise L.MipsFusionB200Error("MLP_reg parameters must live on a CUDA device (no CPU fallback)")
+            flat = self.flat_weights()
+            prep = torch.empty(int(L.lib().mf_mlp_prep_size()), device=dev, dtype=torch.float32)
+            L.call("mf_mlp_prepare", L.ptr(flat), L.ptr(prep), L.stream())
+            cache = (key, prep)
+            self.__dict__["_prep_cache"] = cache
+        return cache[1]
+
+    def __getstate__(self):
+        s = self.__dict__.copy()
+        s.pop("_prep_cache", None)
+        return s
+
+
+    def forward(self, embed, embed_pos, query_pts):
+        dev = self.pts_linear[0].weight.device
+        return _MLPFn.apply(L.f32c(embed, dev), L.f32c(embed_pos, dev), L.f32c(query_pts, dev), self.prepared(), *self.ordered_params())

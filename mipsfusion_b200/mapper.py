@@ -1,0 +1,136 @@
+"""Fused mapping step: the body of the reference's BA loops (mipsfusion.py:293-335, first_frame_mapping
+:176-193, InactiveMap.local_BA :250-260) -- forward, loss, backward, Adam, zero_grad -- issued as a fixed
+sequence of kernels on persistent buffers, with no autograd graph, no allocation and no host sync.
+
+``JointEncoding.forward`` + ``loss.backward()`` + ``optimizer.step()`` stays available as the drop-in
+route; this class is the fast route the online system uses once the model lives on the GPU.  With a
+process group it becomes data parallel over ray batches: the global mask counts are all-reduced before
+the loss (helper_functions/utils.py:43-47 uses batch-global counts) and the gradients after the backward.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from .decoder import _Workspace
+
+
+class FusedMapper:
+    def __init__(self, model, lr_decoder=None, lr_embed=None, group=None):
+        self.model = model
+        cfg = model.config
+        self.dev = model._device
+        if self.dev.type != "cuda":
+            raise L.MipsFusionB200Error("FusedMapper needs the model on a CUDA device")
+        self.lr_decoder = cfg["mapping"]["lr_decoder"] if lr_decoder is None else lr_decoder
+        self.lr_embed = cfg["mapping"]["lr_embed"] if lr_embed is None else lr_embed
+        self.group = group
+        self.world = 1
+        if group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(group)
+        t = cfg["training"]
+        # d(total loss)/d(rgb, depth, sdf, fs loss): the weights of get_loss_from_ret (mipsfusion.py:142-152)
+        self.loss_w = torch.tensor([t["rgb_weight"], t["depth_weight"], t["sdf_weight"], t["fs_weight"]], dtype=torch.float32,
+                                   device=self.dev)
+        self.grid = model.embed_fn.params.data
+        self.mlp = model.decoder.flat_weights().contiguous()            # master copy while stepping
+        self.prep = torch.empty(int(L.lib().mf_mlp_prep_size()), device=self.dev, dtype=torch.float32)
+        self.g_grid = torch.zeros_like(self.grid); self.m_grid = torch.zeros_like(self.grid); self.v_grid = torch.zeros_like(self.grid)
+        self.g_mlp = torch.zeros_like(self.mlp); self.m_mlp = torch.zeros_like(self.mlp); self.v_mlp = torch.zeros_like(self.mlp)
+        self.step_count = 0
+        self._bufs = {}
+        self.timing = None            # optional dict name -> (start_event, end_event) lists
+        self.launches = 0
+        with torch.cuda.device(self.dev):
+            L.call("mf_mlp_prepare", L.ptr(self.mlp), L.ptr(self.prep), L.stream())
+
+    def _buffers(self, R, S):
+        key = (R, S)
+        b = self._bufs.get(key)
+        if b is None:
+            d = self.dev
+            f32 = dict(device=d, dtype=torch.float32)
+            b = dict(z=torch.empty(R, S, **f32), counts=torch.empty(2, device=d, dtype=torch.int64),
+                     raw=torch.empty(R, S, L.MF_RAW_DIM, **f32), d_raw=torch.empty(R, S, L.MF_RAW_DIM, **f32),
+                     rgb=torch.empty(R, 3, **f32), depth=torch.empty(R, **f32), losses=torch.zeros(8, **f32),
+                     scratch=torch.empty(R * 8, **f32), u=torch.empty(R, S, **f32))
+            self._bufs[key] = b
+        return b
+
+    def _field(self):
+        f = self.model._field(keep=(self.grid, self.prep))
+        return f
+
+    def step(self, rays_o, rays_d, target_rgb, target_d, u=None, EMD_w=0.01, update=True):
+        """One mapping iteration on device tensors (rays_o/rays_d (R,3), target_rgb (R,3), target_d (R,) or (R,1)).
+        Returns the (8,) device tensor [rgb_loss, depth_loss, sdf_loss, fs_loss, psnr, fs_w, sdf_w, n_valid]."""
+        model = self.model
+        R = rays_o.shape[0]
+        cfg, lins = model._render_cfg(True, EMD_w, self.dev)
+        S = cfg.n_samples_d + cfg.n_range_d
+        b = self._buffers(R, S)
+        st = L.stream()
+        field = self._field()
+        target_d = target_d.reshape(R)
+        if cfg.perturb:
+            if u is None:
+                u = b["u"].uniform_()                  # the reference's torch.rand(z_vals.shape), drawn on the device
+        else:
+            u = None
+        tm = self.timing
+        def ev():
+            if tm is None:
+                return None
+            e = torch.cuda.Event(enable_timing=True); e.record(); return e
+        e0 = ev()
+        L.call("mf_sample_z", L.ptr(target_d), L.ptr(u), L.ptr(lins[0]), L.ptr(lins[1]), L.ptr(lins[2]), C.byref(cfg),
+               L.ptr(b["z"]), L.ptr(b["counts"]), R, st)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(b["counts"], group=self.group)           # batch-global mask counts
+        e1 = ev()
+        L.call("mf_field_query_rays", L.ptr(rays_o), L.ptr(rays_d), L.ptr(b["z"]), C.byref(field), L.ptr(b["raw"]), R, S, st)
+        e2 = ev()
+        L.call("mf_render_loss_fwd", L.ptr(b["raw"]), L.ptr(b["z"]), L.ptr(target_rgb), L.ptr(target_d), L.ptr(b["counts"]),
+               C.byref(cfg), L.ptr(b["rgb"]), L.ptr(b["depth"]), None, None, None, L.ptr(b["losses"]), L.ptr(b["scratch"]), R, S, st)
+        L.call("mf_render_loss_bwd", L.ptr(b["raw"]), L.ptr(b["z"]), L.ptr(target_rgb), L.ptr(target_d), L.ptr(b["counts"]),
+               L.ptr(b["losses"]), C.byref(cfg), L.ptr(self.loss_w), None, None, L.ptr(b["d_raw"]), R, S, st)
+        e3 = ev()
+        L.call("mf_field_query_rays_bwd", L.ptr(rays_o), L.ptr(rays_d), L.ptr(b["z"]), C.byref(field), L.ptr(b["d_raw"]),
+               L.ptr(self.g_grid), L.ptr(self.g_mlp), None, None, L.ptr(_Workspace.get(self.dev)), R, S, st)
+        e4 = ev()
+        self.launches += 7
+        if update:
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(self.g_grid, group=self.group)
+                dist.all_reduce(self.g_mlp, group=self.group)
+                self.g_grid.mul_(1.0 / self.world); self.g_mlp.mul_(1.0 / self.world)
+            self.apply_gradients()
+        e5 = ev()
+        if tm is not None:
+            for name, a, c in (("sample_z", e0, e1), ("field_fwd", e1, e2), ("render_loss", e2, e3), ("field_bwd", e3, e4),
+                               ("adam", e4, e5)):
+                tm.setdefault(name, []).append((a, c))
+        return b["losses"]
+
+    def apply_gradients(self):
+        """Adam on (grid, decoder) with the reference's groups (mipsfusion.py:580-584), zero_grad fused in."""
+        self.step_count += 1
+        st = L.stream()
+        L.call("mf_adam_step", L.ptr(self.grid), L.ptr(self.g_grid), L.ptr(self.m_grid), L.ptr(self.v_grid), self.grid.numel(),
+               float(self.lr_embed), 0.9, 0.99, 1e-15, 0.0, self.step_count, 1, st)
+        L.call("mf_adam_step", L.ptr(self.mlp), L.ptr(self.g_mlp), L.ptr(self.m_mlp), L.ptr(self.v_mlp), self.mlp.numel(),
+               float(self.lr_decoder), 0.9, 0.99, 1e-8, 1e-6, self.step_count, 1, st)
+        L.call("mf_mlp_prepare", L.ptr(self.mlp), L.ptr(self.prep), st)
+        self.launches += 4
+
+    def sync_to_module(self):
+        """Write the stepped decoder weights back into the module's nn.Parameters (the grid is updated in place)."""
+        o = 0
+        with torch.no_grad():
+            for p in self.model.decoder.ordered_params():
+                n = p.numel()
+                p.copy_(self.mlp[o:o + n].view(p.shape))
+                o += n

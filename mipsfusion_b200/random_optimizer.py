@@ -1,0 +1,121 @@
+"""Drop-in for reference RandomOptimizer.py: particle-swarm-template pose search whose hot loop
+(candidate transform -> field query -> per-candidate fitness -> swarm update) runs as CUDA kernels
+(mf_ro_score / mf_ro_update) with no host synchronisation inside the iteration loop.
+
+Candidates shard naturally across GPUs: pass ``group`` (a torch.distributed process group) and every
+rank scores C/G candidates, followed by one small all-gather of (fitness, mean_sdf, pst7)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .sampling_helper import sample_pixels_uniformly
+
+
+def pose_compose(rot_mat, trans_vec):
+    """reference helper_functions/geometry_helper.py:43-47 (returns a CPU tensor)."""
+    T = torch.eye(4)
+    T[:3, :3] = rot_mat
+    T[:3, 3] = trans_vec.squeeze()
+    return T
+
+
+class RandomOptimizer:
+    def __init__(self, cfg, mipsfusion, particles=None, group=None):
+        self.cfg = cfg
+        self.slam = mipsfusion
+        self.dataset = self.slam.dataset
+        self.device = torch.device(self.slam.device)
+        ro = self.cfg["tracking"]["RO"]
+        self.particle_size = ro["particle_size"]
+        self.scaling_coefficient1 = ro["initial_scaling_factor"]
+        self.scaling_coefficient2 = ro["rescaling_factor"]
+        self.sdf_weight = 1000.
+        self.trunc_value = self.cfg["training"]["trunc"]
+        if particles is None:                                      # RandomOptimizer.py:26-32
+            particles = np.random.multivariate_normal(np.zeros(6), np.eye(6), self.particle_size).astype(np.float32)
+            particles = torch.from_numpy(particles)
+            particles[0, :] = 0
+            particles = torch.clamp(particles, -2., 2.)
+        self.pre_sampled_particle = L.f32c(torch.as_tensor(particles), self.device)
+        self.iW = self.cfg["tracking"]["ignore_edge_W"]
+        self.iH = self.cfg["tracking"]["ignore_edge_H"]
+        self.rays_dir = L.f32c(self.dataset.rays_d, self.device)   # (H, W, 3) camera-frame directions
+        self.row_indices, self.col_indices = sample_pixels_uniformly(self.dataset.H, self.dataset.W, ro["n_rows"], ro["n_cols"],
+                                                                     device=self.device)
+        self.fx, self.fy, self.cx, self.cy = self.dataset.fx, self.dataset.fy, self.dataset.cx, self.dataset.cy
+        self.group = group
+        self.last_info = None          # per-iteration (count, success, argmin) of the last optimize() call
+        self.last_fitness = None
+
+    # ---- sharding ---------------------------------------------------------------------------------
+    def _shard(self):
+        Cn = self.pre_sampled_particle.shape[0]
+        if self.group is None:
+            return 0, Cn, 1, 0
+        import torch.distributed as dist
+        ws, rk = dist.get_world_size(self.group), dist.get_rank(self.group)
+        per = (Cn + ws - 1) // ws
+        b = min(rk * per, Cn)
+        return b, min(per, Cn - b), ws, rk
+
+    def score(self, model, rot_cur, trans_cur, search_size, target_d, rays_d_cam):
+        """Fitness of every candidate (RandomOptimizer.py:113-131).  All arguments are device tensors:
+        rot_cur (3,3), trans_cur (3), search_size (6), target_d (P), rays_d_cam (P,3).
+        -> fitness (C), mean_sdf (C), pst7 (C,7)."""
+        dev = self.device
+        Cn, P = self.pre_sampled_particle.shape[0], target_d.shape[0]
+        b, n, ws, rk = self._shard()
+        per = (Cn + ws - 1) // ws
+        packed = torch.zeros(per, 9, device=dev, dtype=torch.float32)        # [fitness, mean_sdf, pst7]
+        fit = torch.empty(per, device=dev); msdf = torch.empty(per, device=dev); pst7 = torch.empty(per, 7, device=dev)
+        scratch = torch.empty(max(n, 1) * (P + 12), device=dev, dtype=torch.float32)
+        field = model._field()
+        with torch.cuda.device(dev):
+            L.call("mf_ro_score", L.ptr(self.pre_sampled_particle), L.ptr(search_size), L.ptr(rot_cur), L.ptr(trans_cur),
+                   L.ptr(rays_d_cam), L.ptr(target_d), C.byref(field), float(self.trunc_value), float(self.sdf_weight),
+                   int(b), int(n), int(P), L.ptr(fit), L.ptr(msdf), L.ptr(pst7), L.ptr(scratch), L.stream())
+        if ws == 1:
+            return fit[:Cn], msdf[:Cn], pst7[:Cn]
+        import torch.distributed as dist
+        packed[:, 0], packed[:, 1], packed[:, 2:] = fit, msdf, pst7
+        gathered = torch.empty(ws * per, 9, device=dev, dtype=torch.float32)
+        dist.all_gather_into_tensor(gathered, packed, group=self.group)
+        gathered = gathered[:Cn]
+        return gathered[:, 0].contiguous(), gathered[:, 1].contiguous(), gathered[:, 2:].contiguous()
+
+    def update(self, fitness, mean_sdf, pst7, rot_cur, trans_cur, search_size):
+        """Steps 3-5 of the loop body (RandomOptimizer.py:202-224), in place on the device state."""
+        dev = self.device
+        Cn = fitness.shape[0]
+        better = torch.empty(Cn, device=dev, dtype=torch.uint8)
+        info = torch.empty(4, device=dev, dtype=torch.int32)
+        with torch.cuda.device(dev):
+            L.call("mf_ro_update", L.ptr(fitness), L.ptr(mean_sdf), L.ptr(pst7), int(Cn), float(self.scaling_coefficient2),
+                   L.ptr(rot_cur), L.ptr(trans_cur), L.ptr(search_size), L.ptr(better), L.ptr(info), L.stream())
+        return better, info
+
+    @torch.no_grad()
+    def optimize(self, model, depth_img, initial_pose, last_frame_pose, n_iter=10):
+        """reference RandomOptimizer.py:165-227; returns the tracked pose as a CPU (4,4) tensor."""
+        if n_iter <= 0:
+            return initial_pose
+        dev = self.device
+        init = L.f32c(torch.as_tensor(initial_pose), dev)
+        rot_cur = init[:3, :3].contiguous()
+        trans_cur = init[:3, 3].contiguous()
+        search = torch.full((6,), float(self.scaling_coefficient1), device=dev, dtype=torch.float32)
+        depth = L.f32c(torch.as_tensor(depth_img), dev)            # one H2D copy of the depth image
+        infos, fits, betters = [], [], []
+        for i in range(n_iter):
+            off = i % 5
+            ih, iw = self.row_indices + off, self.col_indices + off
+            target_d = depth[ih, iw].contiguous()
+            rays_d_cam = self.rays_dir[ih, iw, :].contiguous()
+            fit, msdf, pst7 = self.score(model, rot_cur, trans_cur, search, target_d, rays_d_cam)
+            better, info = self.update(fit, msdf, pst7, rot_cur, trans_cur, search)
+            infos.append(info); fits.append(fit); betters.append(better)
+        self.last_info = torch.stack(infos)        # device tensors; reading them is the caller's sync point
+        self.last_fitness, self.last_better = fits, betters
+        return pose_compose(rot_cur.cpu(), trans_cur.cpu())

@@ -1,0 +1,307 @@
+"""Drop-in for reference model/scene_rep.py: ``JointEncoding`` (one submap's neural field).
+
+Same constructor, attributes (``embed_fn``, ``embedpos_fn``, ``decoder``, ``bounding_box``,
+``coords_norm_factor``, ``config``), methods and returned dict keys as the reference
+(model/scene_rep.py:11-238), so that ActiveMap / InactiveMap / RandomOptimizer / Mesher call it
+unchanged.  ``forward`` / ``render_rays`` / ``run_network`` / ``query_*`` run as fused sm_100a
+kernels: sample z -> (normalise + hash-grid + frequency encode + MLP) -> SDF-to-weight render ->
+losses, with a hand-written backward to the grid, the decoder and the rays (pose gradients).
+
+The reference draws the stratified jitter with CPU ``torch.rand`` (scene_rep.py:176); here it is
+drawn on the device unless the caller passes ``u`` explicitly (the parity tests do).
+"""
+import copy
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .decoder import MLP_reg, _Workspace
+from .encodings import get_encoder
+
+
+def _linspace(a, b, n, device):
+    # evaluated by torch on the CPU exactly as the reference does (scene_rep.py:158-166), then shipped
+    return torch.linspace(a, b, steps=n).to(device=device, dtype=torch.float32).contiguous()
+
+
+class _FieldQueryFn(torch.autograd.Function):
+    """run_network / query_color_sdf: points (N,3) -> (N,10)."""
+
+    @staticmethod
+    def forward(ctx, pts, normalize, model, grid, *mlp_params):
+        field = model._field()
+        N = pts.shape[0]
+        out = torch.empty(N, L.MF_RAW_DIM, device=pts.device, dtype=torch.float32)
+        L.call("mf_field_query", L.ptr(pts), C.byref(field), int(normalize), L.ptr(out), N, L.stream())
+        ctx.model, ctx.normalize = model, normalize
+        ctx.keep = field._keepalive
+        ctx.save_for_backward(pts, grid)
+        ctx.shapes = [p.shape for p in mlp_params]
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        pts, grid = ctx.saved_tensors
+        model = ctx.model
+        field = model._field(ctx.keep)
+        N = pts.shape[0]
+        g_grid = torch.zeros_like(grid)
+        g_mlp = torch.zeros(L.MF_MLP_PARAMS, device=pts.device, dtype=torch.float32)
+        d_pts = torch.empty_like(pts) if ctx.needs_input_grad[0] else None
+        L.call("mf_field_query_bwd", L.ptr(pts), C.byref(field), int(ctx.normalize), L.ptr(d_out.contiguous()), L.ptr(g_grid),
+               L.ptr(g_mlp), L.ptr(d_pts), L.ptr(_Workspace.get(pts.device)), N, L.stream())
+        return (d_pts, None, None, g_grid, *_split(g_mlp, ctx.shapes))
+
+
+def _split(flat, shapes):
+    out, o = [], 0
+    for shp in shapes:
+        n = shp.numel()
+        out.append(flat[o:o + n].view(shp))
+        o += n
+    return out
+
+
+class _RenderFn(torch.autograd.Function):
+    """render_rays (+ losses when targets are given).  Outputs:
+    rgb (R,3), depth (R), aux (R,3)=[depth_var, disp, acc], z (R,S), raw (R,S,10), losses (8)."""
+
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, target_rgb, target_d, u, emd_w, model, grid, *mlp_params):
+        dev = rays_o.device
+        R = rays_o.shape[0]
+        cfg, lins = model._render_cfg(target_d is not None, emd_w, dev)
+        S = cfg.n_samples_d + cfg.n_range_d
+        field = model._field()
+        st = L.stream()
+        z = torch.empty(R, S, device=dev, dtype=torch.float32)
+        counts = torch.empty(2, device=dev, dtype=torch.int64)
+        L.call("mf_sample_z", L.ptr(target_d), L.ptr(u), L.ptr(lins[0]), L.ptr(lins[1]), L.ptr(lins[2]), C.byref(cfg), L.ptr(z),
+               L.ptr(counts), R, st)
+        raw = torch.empty(R, S, L.MF_RAW_DIM, device=dev, dtype=torch.float32)
+        L.call("mf_field_query_rays", L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), C.byref(field), L.ptr(raw), R, S, st)
+        rgb = torch.empty(R, 3, device=dev, dtype=torch.float32)
+        depth = torch.empty(R, device=dev, dtype=torch.float32)
+        aux = torch.empty(R, 3, device=dev, dtype=torch.float32)
+        losses = torch.zeros(8, device=dev, dtype=torch.float32)
+        scratch = torch.empty(R * 8, device=dev, dtype=torch.float32) if target_d is not None else None
+        L.call("mf_render_loss_fwd", L.ptr(raw), L.ptr(z), L.ptr(target_rgb), L.ptr(target_d), L.ptr(counts), C.byref(cfg),
+               L.ptr(rgb), L.ptr(depth), L.ptr(aux), None, None, L.ptr(losses), L.ptr(scratch), R, S, st)
+        ctx.model, ctx.cfg, ctx.S = model, cfg, S
+        ctx.keep = field._keepalive
+        ctx.has_t = target_d is not None
+        ctx.save_for_backward(rays_o, rays_d, target_rgb, target_d, z, raw, counts, losses, grid)
+        ctx.shapes = [p.shape for p in mlp_params]
+        ctx.mark_non_differentiable(aux, z, counts)
+        return rgb, depth, aux, z, raw, losses, counts
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_aux, g_z, g_raw, g_losses, g_counts):
+        rays_o, rays_d, target_rgb, target_d, z, raw, counts, losses, grid = ctx.saved_tensors
+        model, cfg, S = ctx.model, ctx.cfg, ctx.S
+        dev, R = rays_o.device, rays_o.shape[0]
+        st = L.stream()
+        field = model._field(ctx.keep)
+        d_raw = torch.empty_like(raw)
+        gl = g_losses[:4].contiguous() if g_losses is not None else None
+        L.call("mf_render_loss_bwd", L.ptr(raw), L.ptr(z), L.ptr(target_rgb), L.ptr(target_d), L.ptr(counts), L.ptr(losses),
+               C.byref(cfg), L.ptr(gl), L.ptr(g_rgb.contiguous() if g_rgb is not None else None),
+               L.ptr(g_depth.contiguous() if g_depth is not None else None), L.ptr(d_raw), R, S, st)
+        if g_raw is not None:
+            d_raw = d_raw + g_raw
+        want_rays = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        g_grid = torch.zeros_like(grid)
+        g_mlp = torch.zeros(L.MF_MLP_PARAMS, device=dev, dtype=torch.float32)
+        d_o = torch.empty_like(rays_o) if want_rays else None
+        d_d = torch.empty_like(rays_d) if want_rays else None
+        ws = _Workspace.get(dev, 3 * R * S if want_rays else 0)
+        L.call("mf_field_query_rays_bwd", L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), C.byref(field), L.ptr(d_raw), L.ptr(g_grid),
+               L.ptr(g_mlp), L.ptr(d_o), L.ptr(d_d), L.ptr(ws), R, S, st)
+        return (d_o, d_d, None, None, None, None, None, g_grid, *_split(g_mlp, ctx.shapes))
+
+
+class JointEncoding(nn.Module):
+    def __init__(self, config, bound_box, coords_norm_factor):
+        super().__init__()
+        self.config = config
+        self.bounding_box = bound_box
+        self.coords_norm_factor = coords_norm_factor
+        self.get_resolution()
+        self.get_encoding(config)
+        self.get_decoder(config)
+        self.save_initial_param()
+
+    # ---- construction: model/scene_rep.py:24-55 -------------------------------------------------
+    def get_resolution(self):
+        dim_max = (self.bounding_box[:, 1] - self.bounding_box[:, 0]).max()
+        if self.config["grid"]["voxel_sdf"] > 10:
+            self.resolution_sdf = self.config["grid"]["voxel_sdf"]
+        else:
+            self.resolution_sdf = int(dim_max / self.config["grid"]["voxel_sdf"])
+
+    def get_encoding(self, config):
+        self.embedpos_fn, self.input_ch_pos = get_encoder(config["pos"]["enc"], n_bins=self.config["pos"]["n_bins"])
+        self.embed_fn, self.input_ch = get_encoder(config["grid"]["enc"], log2_hashmap_size=config["grid"]["hash_size"],
+                                                   desired_resolution=256)
+
+    def get_decoder(self, config):
+        self.decoder = MLP_reg(config, input_ch=self.input_ch, input_ch_pos=self.input_ch_pos)
+
+    def save_initial_param(self):
+        self.initial_dict = copy.deepcopy(self.state_dict())
+
+    def recover_initial_param(self):
+        self.load_state_dict(self.initial_dict)
+
+    # ---- host-side descriptors -------------------------------------------------------------------
+    def _norm_host(self):
+        """(a, b) fp64 lists with x_n = (x - a) / b, cached per bound tensor (scene_rep.py:138-142)."""
+        key = (id(self.bounding_box), id(self.coords_norm_factor), bool(self.config["grid"]["use_bound_normalize"]),
+               bool(self.config["grid"]["tcnn_encoding"]))
+        cache = self.__dict__.get("_norm_cache")
+        if cache is None or cache[0] != key:
+            if not self.config["grid"]["tcnn_encoding"]:
+                a, b = [0.0] * 3, [1.0] * 3
+            elif self.config["grid"]["use_bound_normalize"]:
+                bb = torch.as_tensor(self.bounding_box).detach().to("cpu", torch.float64)
+                a = bb[:, 0].tolist()
+                b = (bb[:, 1] - bb[:, 0]).tolist()
+            else:
+                nf = torch.as_tensor(self.coords_norm_factor).detach().to("cpu", torch.float64)
+                a = (-nf).tolist()
+                b = (2 * nf).tolist()
+            cache = (key, a, b)
+            self.__dict__["_norm_cache"] = cache
+        return cache[1], cache[2]
+
+    def _field(self, keep=None):
+        """mf_field descriptor of the current weights."""
+        if self.config["pos"]["enc"].lower().find("freq") < 0 or self.config["pos"]["n_bins"] != 8:
+            raise L.MipsFusionB200Error("fused field kernels are built for pos.enc=Frequency, n_bins=8")
+        grid = self.embed_fn.params
+        if not grid.is_cuda:
+            raise L.MipsFusionB200Error("JointEncoding must live on a CUDA device (no CPU fallback); call .to('cuda')")
+        prep = keep[1] if keep is not None else self.decoder.prepared()
+        f = L.Field()
+        f.grid, f.mlp_prep = grid.data_ptr(), prep.data_ptr()
+        a, b = self._norm_host()
+        for k in range(3):
+            f.norm_a[k], f.norm_b[k] = a[k], b[k]
+        f.norm_factor = float(self.config["training"]["norm_factor"])
+        f.meta = self.embed_fn.meta
+        f._keepalive = (grid, prep)
+        return f
+
+    def _render_cfg(self, has_depth, emd_w, device):
+        tr, cam = self.config["training"], self.config["cam"]
+        cfg = L.RenderCfg()
+        if has_depth:
+            cfg.n_samples_d, cfg.n_range_d = int(tr["n_samples_d"]), int(tr["n_range_d"])
+        else:
+            cfg.n_samples_d, cfg.n_range_d = int(tr["n_samples"]), 0
+        cfg.perturb = 1 if tr["perturb"] > 0.0 else 0
+        cfg.rgb_missing_nz = 1 if tr["rgb_missing"] != 0 else 0
+        cfg.trunc, cfg.sc_factor = float(tr["trunc"]), float(self.config["data"]["sc_factor"])
+        cfg.depth_trunc, cfg.emd_w = float(cam["depth_trunc"]), float(emd_w)
+        key = (has_depth, cfg.n_samples_d, cfg.n_range_d, float(cam["near"]), float(cam["far"]), float(tr["range_d"]), str(device))
+        cache = self.__dict__.get("_lin_cache")
+        if cache is None or cache[0] != key:
+            lu = _linspace(cam["near"], cam["far"], cfg.n_samples_d, device) if cfg.n_samples_d > 0 else None
+            lr = _linspace(-tr["range_d"], tr["range_d"], cfg.n_range_d, device) if cfg.n_range_d > 0 else None
+            lf = _linspace(cam["near"], cam["far"], cfg.n_range_d, device) if cfg.n_range_d > 0 else None
+            cache = (key, (lu, lr, lf))
+            self.__dict__["_lin_cache"] = cache
+        return cfg, cache[1]
+
+    def __getstate__(self):
+        s = self.__dict__.copy()
+        for k in ("_norm_cache", "_lin_cache"):
+            s.pop(k, None)
+        return s
+
+    @property
+    def _device(self):
+        return self.embed_fn.params.device
+
+    # ---- queries: model/scene_rep.py:106-146 -----------------------------------------------------
+    def _query(self, pts, normalize):
+        shape = pts.shape
+        flat = L.f32c(pts.reshape(-1, shape[-1]), self._device)
+        out = _FieldQueryFn.apply(flat, normalize, self, self.embed_fn.params, *self.decoder.ordered_params())
+        return out.reshape(*shape[:-1], L.MF_RAW_DIM)
+
+    def query_color_sdf(self, query_points):
+        """(…,3) already-normalised points -> (N,10) rgb_raw + sdf + entropy + prob."""
+        return self._query(query_points, False).reshape(-1, L.MF_RAW_DIM)
+
+    def query_sdf(self, query_points):
+        return self.query_color_sdf(query_points)[..., 3:4]
+
+    def query_color(self, query_points):
+        return torch.sigmoid(self.query_color_sdf(query_points)[..., :3])
+
+    def query_sdf_entropy_prob(self, query_points):
+        return self.query_color_sdf(query_points)[..., 3:]
+
+    def run_network(self, inputs):
+        """(…,3) points in the submap frame -> (…,10); normalisation fused (fp64, as the reference)."""
+        return self._query(inputs, bool(self.config["grid"]["tcnn_encoding"]))
+
+    # ---- rendering: model/scene_rep.py:58-103,153-187 ---------------------------------------------
+    def _render(self, rays_o, rays_d, target_rgb, target_d, u, emd_w):
+        dev = self._device
+        rays_o, rays_d = L.f32c(rays_o, dev), L.f32c(rays_d, dev)
+        R = rays_o.shape[0]
+        if target_d is not None:
+            target_d = L.f32c(target_d, dev).reshape(R)
+        if target_rgb is not None:
+            target_rgb = L.f32c(target_rgb, dev)
+        tr = self.config["training"]
+        S = (tr["n_samples_d"] + tr["n_range_d"]) if target_d is not None else tr["n_samples"]
+        if tr["perturb"] > 0.0:
+            u = torch.rand(R, S, device=dev, dtype=torch.float32) if u is None else L.f32c(u, dev)
+        else:
+            u = None
+        return _RenderFn.apply(rays_o, rays_d, target_rgb, target_d, u, emd_w, self, self.embed_fn.params,
+                               *self.decoder.ordered_params())
+
+    def render_rays(self, rays_o, rays_d, target_d=None, u=None):
+        rgb, depth, aux, z, raw, _, _ = self._render(rays_o, rays_d, None, target_d, u, 0.0)
+        return {"rgb": rgb, "depth": depth, "disp_map": aux[:, 1], "acc_map": aux[:, 2], "depth_var": aux[:, 0],
+                "z_vals": z, "raw": raw}
+
+    def sdf2weights(self, sdf, z_vals, args=None):
+        raw = torch.zeros(*sdf.shape, L.MF_RAW_DIM, device=self._device, dtype=torch.float32)
+        raw[..., 3] = sdf
+        return self._raw2outputs(raw, z_vals, args)[3]
+
+    def raw2outputs(self, raw, z_vals):
+        return self._raw2outputs(raw, z_vals, None)
+
+    def _raw2outputs(self, raw, z_vals, args):
+        """(no autograd) -> rgb_map, disp_map, acc_map, weights, depth_map, depth_var."""
+        dev = self._device
+        raw10 = raw
+        if raw.shape[-1] != L.MF_RAW_DIM:                    # the reference passes (R,S,4+) slices
+            raw10 = torch.zeros(*raw.shape[:-1], L.MF_RAW_DIM, device=dev, dtype=torch.float32)
+            raw10[..., :raw.shape[-1]] = raw
+        raw10, z = L.f32c(raw10.detach(), dev), L.f32c(z_vals.detach(), dev)
+        R, S = z.shape
+        cfg, _ = self._render_cfg(True, 0.0, dev)
+        if args is not None:
+            cfg.trunc, cfg.sc_factor = float(args["training"]["trunc"]), float(args["data"]["sc_factor"])
+        rgb = torch.empty(R, 3, device=dev); depth = torch.empty(R, device=dev); aux = torch.empty(R, 3, device=dev)
+        w = torch.zeros(R, S, device=dev)
+        L.call("mf_render_loss_fwd", L.ptr(raw10), L.ptr(z), None, None, None, C.byref(cfg), L.ptr(rgb), L.ptr(depth), L.ptr(aux),
+               L.ptr(w), None, None, None, R, S, L.stream())
+        return rgb, aux[:, 1], aux[:, 2], w, depth, aux[:, 0]
+
+    # ---- training forward: model/scene_rep.py:190-238 --------------------------------------------
+    def forward(self, rays_o, rays_d, target_rgb, target_d, EMD_w=0.01, u=None):
+        if not self.training:
+            return self.render_rays(rays_o, rays_d, target_d=target_d, u=u)
+        rgb, depth, aux, z, raw, losses, counts = self._render(rays_o, rays_d, target_rgb, target_d, u, EMD_w)
+        return {"rgb": rgb, "depth": depth, "rgb_loss": losses[0], "depth_loss": losses[1], "sdf_loss": losses[2],
+                "fs_loss": losses[3], "psnr": losses[4].detach()}

@@ -1,0 +1,176 @@
+"""GPU parity: JointEncoding (query, z sampling, render, losses, backward, Adam) against the oracle
+and against vectors produced by the reference's own code (tests/golden/scene.npz)."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from oracle import adam as oadam
+
+pytestmark = pytest.mark.gpu
+FIELD_RTOL = 1e-3            # BASELINE.json: rel 1e-3 on fields, losses and gradients
+
+
+def test_scene_golden_forward_backward(golden):
+    fx = golden("scene")
+    cfg = H.make_config(int(fx["hash_size"]))
+    model = H.cuda_model(cfg, H.fixture_state(fx))
+    rays = H.T(fx["rays"])
+    ro = H.T(fx["rays_o"]).cuda().requires_grad_(True)
+    rd = H.T(fx["rays_d"]).cuda().requires_grad_(True)
+    u = H.T(fx["u"]).cuda()
+    ret = model(ro, rd, rays[:, 3:6].cuda(), rays[:, 6:7].cuda(), u=u)
+    assert set(ret.keys()) == {"rgb", "depth", "rgb_loss", "depth_loss", "sdf_loss", "fs_loss", "psnr"}
+    for k in ("rgb_loss", "depth_loss", "sdf_loss", "fs_loss", "psnr"):
+        np.testing.assert_allclose(float(ret[k]), float(fx[k]), rtol=1e-4, err_msg=k)
+    assert H.rel_err(ret["rgb"].detach().cpu(), fx["rgb"]) < 1e-4
+    assert H.rel_err(ret["depth"].detach().cpu(), fx["depth"]) < 1e-4
+    t = cfg["training"]
+    loss = t["rgb_weight"] * ret["rgb_loss"] + t["sdf_weight"] * ret["sdf_loss"] + t["fs_weight"] * ret["fs_loss"]
+    np.testing.assert_allclose(float(loss), float(fx["loss"]), rtol=1e-4)
+    loss.backward()
+    assert H.rel_err(model.embed_fn.params.grad.cpu(), fx["g:embed_fn.params"]) < FIELD_RTOL
+    for name, p in model.decoder.named_parameters():
+        assert H.rel_err(p.grad.cpu(), fx["g:decoder." + name]) < FIELD_RTOL, name
+    assert H.rel_err(ro.grad.cpu(), fx["g_rays_o"]) < FIELD_RTOL
+    assert H.rel_err(rd.grad.cpu(), fx["g_rays_d"]) < FIELD_RTOL
+    # eval-mode render dict + z bit-exact + point queries
+    model.eval()
+    rend = model(ro.detach(), rd.detach(), None, rays[:, 6:7].cuda(), u=u)
+    assert set(rend.keys()) == {"rgb", "depth", "disp_map", "acc_map", "depth_var", "z_vals", "raw"}
+    assert np.array_equal(rend["z_vals"].cpu().numpy(), fx["z_vals"])             # same fp32 op order as torch
+    assert H.rel_err(rend["raw"].cpu(), fx["raw"]) < 1e-4
+    for k in ("depth_var", "acc_map", "disp_map"):
+        assert H.rel_err(rend[k].cpu(), fx[k]) < 1e-4, k
+    q = model.run_network(H.T(fx["q_pts"]).cuda())
+    assert H.rel_err(q.detach().cpu(), fx["q_out"]) < 1e-4
+    assert model.query_sdf(torch.rand(7, 3).cuda()).shape == (7, 1)
+
+
+@pytest.mark.parametrize("R,S,nsd,nrd,T,bound", [(512, 43, 32, 11, 19, True), (300, 75, 50, 25, 16, False), (1, 43, 32, 11, 14, True)])
+def test_scene_vs_oracle(R, S, nsd, nrd, T, bound):
+    cfg = H.make_config(T, n_samples_d=nsd, n_range_d=nrd)
+    cfg["grid"]["use_bound_normalize"] = bound
+    if not bound:
+        cfg["mapping"]["localMLP_max_len"] = [7.0, 7.0, 4.0]
+    of = H.oracle_field(cfg, grid_scale=0.3, seed=R)
+    model = H.cuda_model(cfg, H.state_of(of))
+    rays_o, rays_d, rgb, d, u = H.synth_batch(R, S, seed=R, invalid=min(3, R - 1))
+    roo = rays_o.clone().requires_grad_(True); rdo = rays_d.clone().requires_grad_(True)
+    ret_o = of.forward(roo, rdo, rgb, d, u)
+    of.total_loss(ret_o).backward()
+    ro = rays_o.cuda().requires_grad_(True); rd = rays_d.cuda().requires_grad_(True)
+    ret = model(ro, rd, rgb.cuda(), d.cuda(), u=u.cuda())
+    t = cfg["training"]
+    (t["rgb_weight"] * ret["rgb_loss"] + t["sdf_weight"] * ret["sdf_loss"] + t["fs_weight"] * ret["fs_loss"]).backward()
+    for k in ("rgb_loss", "depth_loss", "sdf_loss", "fs_loss"):
+        np.testing.assert_allclose(float(ret[k]), float(ret_o[k]), rtol=FIELD_RTOL, err_msg=k)
+    assert H.rel_err(ret["rgb"].detach().cpu(), ret_o["rgb"].detach()) < FIELD_RTOL
+    assert H.rel_err(ret["depth"].detach().cpu(), ret_o["depth"].detach()) < FIELD_RTOL
+    assert H.rel_err(model.embed_fn.params.grad.cpu(), of.grid.grad) < FIELD_RTOL
+    for name, p in model.decoder.named_parameters():
+        assert H.rel_err(p.grad.cpu(), of.w[name].grad) < FIELD_RTOL, name
+    assert H.rel_err(ro.grad.cpu(), roo.grad) < FIELD_RTOL
+    assert H.rel_err(rd.grad.cpu(), rdo.grad) < FIELD_RTOL
+
+
+def test_integer_streams_bit_exact():
+    """z values, first-sign-change index and the global mask counts (integer work) match the oracle."""
+    import ctypes as C
+    from mipsfusion_b200 import _lib as L
+    cfg = H.make_config(14, n_samples_d=32, n_range_d=11)
+    of = H.oracle_field(cfg, grid_scale=0.5, seed=5)
+    model = H.cuda_model(cfg, H.state_of(of))
+    R, S = 777, 43
+    rays_o, rays_d, rgb, d, u = H.synth_batch(R, S, seed=4, invalid=9)
+    with torch.no_grad():
+        ret_o = of.forward(rays_o, rays_d, rgb, d, u)
+    rgb_c, depth_c, aux, z, raw, losses, counts = model._render(rays_o.cuda(), rays_d.cuda(), rgb.cuda(), d.cuda(), u.cuda(), 0.01)
+    assert np.array_equal(z.cpu().numpy(), ret_o["z_vals"].numpy())
+    assert list(counts.cpu().numpy()) == list(ret_o["counts"])
+    # sign-change index on the oracle's own raw values (so a 1-ulp sdf difference cannot flip it)
+    cfg_c, _ = model._render_cfg(True, 0.01, torch.device("cuda"))
+    raw_o = ret_o["raw"].cuda().contiguous()
+    inds = torch.empty(R, device="cuda", dtype=torch.int32)
+    o3 = torch.empty(R, 3, device="cuda"); o1 = torch.empty(R, device="cuda")
+    L.call("mf_render_loss_fwd", L.ptr(raw_o), L.ptr(z), None, None, None, C.byref(cfg_c), L.ptr(o3), L.ptr(o1), None, None,
+           L.ptr(inds), None, None, R, S, L.stream())
+    assert np.array_equal(inds.cpu().numpy().astype(np.int64), ret_o["inds"].numpy())
+    w = model.raw2outputs(raw_o, z)[3]
+    sums = w.sum(-1).cpu().numpy()
+    assert np.all((np.abs(sums - 1.0) < 1e-4) | (sums < 1e-6))                     # weights are L1-normalised
+
+
+def test_full_size_properties():
+    """BASELINE C1 shape (4096 x 43, T=2^19): size-independent properties instead of an oracle run."""
+    cfg = H.make_config(19, n_samples_d=32, n_range_d=11)
+    of = H.oracle_field(cfg, grid_scale=0.2, seed=2)
+    model = H.cuda_model(cfg, H.state_of(of))
+    R, S = 4096, 43
+    rays_o, rays_d, rgb, d, u = H.synth_batch(R, S, seed=8)
+    args = [t.cuda() for t in (rays_o, rays_d, rgb, d)]
+    ret = model(*args, u=u.cuda())
+    for k in ("rgb_loss", "depth_loss", "sdf_loss", "fs_loss"):
+        assert np.isfinite(float(ret[k])), k
+    (1000 * ret["sdf_loss"] + 10 * ret["fs_loss"] + ret["rgb_loss"]).backward()
+    g1 = model.embed_fn.params.grad.clone(); m1 = model.decoder.pts_linear[2].weight.grad.clone()
+    model.zero_grad(set_to_none=True)
+    ret = model(*args, u=u.cuda())
+    (2 * (1000 * ret["sdf_loss"] + 10 * ret["fs_loss"] + ret["rgb_loss"])).backward()
+    # linearity of the backward in the upstream gradient (atomics reorder sums -> small tolerance)
+    assert H.rel_err(model.embed_fn.params.grad.cpu(), (2 * g1).cpu()) < 1e-4
+    assert H.rel_err(model.decoder.pts_linear[2].weight.grad.cpu(), (2 * m1).cpu()) < 1e-4
+    # a sub-batch of the full batch agrees with the oracle
+    sub = slice(0, 256)
+    with torch.no_grad():
+        raw_o = of.run_network((rays_o[sub, None, :] + rays_d[sub, None, :] * torch.linspace(0.3, 3.0, 16)[None, :, None]))
+        raw_c = model.run_network((args[0][sub, None, :] + args[1][sub, None, :] * torch.linspace(0.3, 3.0, 16).cuda()[None, :, None]))
+    assert H.rel_err(raw_c.cpu(), raw_o) < FIELD_RTOL
+
+
+def test_adam_matches_torch_and_oracle():
+    import mipsfusion_b200 as mf
+    g = torch.Generator().manual_seed(2)
+    for eps, wd, n in ((1e-15, 0.0, 100003), (1e-8, 1e-6, 36577)):
+        p0 = torch.randn(n, generator=g)
+        pt = p0.clone().requires_grad_(True)
+        pc = p0.clone().cuda().requires_grad_(True)
+        ot = torch.optim.Adam([{"params": [pt], "eps": eps, "weight_decay": wd, "lr": 1e-2}], betas=(0.9, 0.99))
+        oc = mf.FusedAdam([{"params": [pc], "eps": eps, "weight_decay": wd, "lr": 1e-2}], betas=(0.9, 0.99))
+        q, m, v = p0.clone(), torch.zeros(n), torch.zeros(n)
+        for step in range(1, 7):
+            grad = torch.randn(n, generator=g) * (0 if step == 3 else 1) * 1e-3
+            pt.grad = grad.clone(); pc.grad = grad.clone().cuda()
+            ot.step(); oc.step(zero_grad=True)
+            oadam.adam_step(q, grad, m, v, step, 1e-2, 0.9, 0.99, eps, wd)
+            assert float(pc.grad.abs().sum()) == 0.0
+        np.testing.assert_allclose(pc.detach().cpu().numpy(), pt.detach().numpy(), rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(pc.detach().cpu().numpy(), q.numpy(), rtol=2e-6, atol=1e-7)
+
+
+def test_training_loop_parity():
+    """30 mapping steps (forward + backward + Adam) track the oracle's loss curve and end at the same weights."""
+    import mipsfusion_b200 as mf
+    cfg = H.make_config(12, n_samples_d=32, n_range_d=11)
+    of = H.oracle_field(cfg, seed=7)
+    model = H.cuda_model(cfg, H.state_of(of))
+    R, S = 256, 43
+    rays_o, rays_d, rgb, d, _ = H.synth_batch(R, S, seed=11)
+    opt_o = oadam.make_optimizer(of)
+    opt_c = mf.create_map_optimizer(model, 1e-2, 1e-2)
+    g = torch.Generator().manual_seed(0)
+    args = [t.cuda() for t in (rays_o, rays_d, rgb, d)]
+    t = cfg["training"]
+    lo, lc = [], []
+    for it in range(30):
+        u = torch.rand(R, S, generator=g)
+        opt_o.zero_grad()
+        ret_o = of.forward(rays_o, rays_d, rgb, d, u)
+        loss_o = of.total_loss(ret_o); loss_o.backward(); opt_o.step()
+        ret = model(*args, u=u.cuda())
+        loss = t["rgb_weight"] * ret["rgb_loss"] + t["sdf_weight"] * ret["sdf_loss"] + t["fs_weight"] * ret["fs_loss"]
+        loss.backward(); opt_c.step(zero_grad=True)
+        lo.append(float(loss_o)); lc.append(float(loss))
+    np.testing.assert_allclose(lc, lo, rtol=5e-3)
+    assert lc[-1] < lc[0]
+    assert H.rel_err(model.decoder.pts_linear[0].weight.detach().cpu(), of.w["pts_linear.0.weight"].detach()) < 2e-2
