@@ -46,8 +46,10 @@ class _MLPFn(torch.autograd.Function):
         want_dx = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         d_pos = torch.empty_like(embed_pos) if want_dx else None
         d_pts = torch.empty_like(pts) if want_dx else None
-        L.call("mf_mlp_bwd", L.ptr(embed), L.ptr(embed_pos), L.ptr(pts), L.ptr(prep), L.ptr(d_out.contiguous()), L.ptr(g_mlp),
-               L.ptr(d_embed), L.ptr(d_pos), L.ptr(d_pts), L.ptr(_Workspace.get(dev)), N, L.stream())
+        d_out = d_out.contiguous()
+        ws = _Workspace.get(dev)
+        L.call("mf_mlp_bwd", L.ptr(embed), L.ptr(embed_pos), L.ptr(pts), L.ptr(prep), L.ptr(d_out), L.ptr(g_mlp),
+               L.ptr(d_embed), L.ptr(d_pos), L.ptr(d_pts), L.ptr(ws), N, L.stream())
         grads, o = [], 0
         for shp in ctx.shapes:
             n = shp.numel()

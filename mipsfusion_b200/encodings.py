@@ -83,7 +83,7 @@ class HashGridEncoding(torch.nn.Module):
         N = x.shape[0]
         out = torch.empty(N, self.n_output_dims, device=x.device, dtype=torch.float32)
         idx = torch.empty(N, self.cfg["n_levels"], 8, device=x.device, dtype=torch.int32)
-        L.call("mf_hashgrid_fwd", L.ptr(x), L.ptr(self.params.detach()), C.byref(self.meta), L.ptr(out), L.ptr(idx), N, L.stream())
+        L.call("mf_hashgrid_fwd", L.ptr(x), L.ptr(self.params.data), C.byref(self.meta), L.ptr(out), L.ptr(idx), N, L.stream())
         return idx.to(torch.int64) & 0xFFFFFFFF, out
 
 
@@ -101,7 +101,8 @@ class _FreqFn(torch.autograd.Function):
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
         dx = torch.empty_like(x)
-        L.call("mf_freq_bwd", L.ptr(x), L.ptr(dy.contiguous()), L.ptr(dx), x.shape[1], ctx.n_freq, x.shape[0], L.stream())
+        dy = dy.contiguous()
+        L.call("mf_freq_bwd", L.ptr(x), L.ptr(dy), L.ptr(dx), x.shape[1], ctx.n_freq, x.shape[0], L.stream())
         return dx, None
 
 

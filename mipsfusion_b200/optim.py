@@ -34,6 +34,7 @@ class FusedAdam(torch.optim.Optimizer):
                     L.call("mf_adam_step", L.ptr(p), L.ptr(g), L.ptr(st["exp_avg"]), L.ptr(st["exp_avg_sq"]), p.numel(),
                            float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
                            int(st["step"]), 1 if zero_grad else 0, L.stream())
+                torch.autograd.graph.increment_version(p)      # the kernel wrote p behind autograd's back
         return None
 
 

@@ -50,8 +50,10 @@ class _FieldQueryFn(torch.autograd.Function):
         g_grid = torch.zeros_like(grid)
         g_mlp = torch.zeros(L.MF_MLP_PARAMS, device=pts.device, dtype=torch.float32)
         d_pts = torch.empty_like(pts) if ctx.needs_input_grad[0] else None
-        L.call("mf_field_query_bwd", L.ptr(pts), C.byref(field), int(ctx.normalize), L.ptr(d_out.contiguous()), L.ptr(g_grid),
-               L.ptr(g_mlp), L.ptr(d_pts), L.ptr(_Workspace.get(pts.device)), N, L.stream())
+        d_out = d_out.contiguous()                     # bound to a name: a temporary could be recycled before the launch
+        ws = _Workspace.get(pts.device)
+        L.call("mf_field_query_bwd", L.ptr(pts), C.byref(field), int(ctx.normalize), L.ptr(d_out), L.ptr(g_grid),
+               L.ptr(g_mlp), L.ptr(d_pts), L.ptr(ws), N, L.stream())
         return (d_pts, None, None, g_grid, *_split(g_mlp, ctx.shapes))
 
 
@@ -106,9 +108,10 @@ class _RenderFn(torch.autograd.Function):
         field = model._field(ctx.keep)
         d_raw = torch.empty_like(raw)
         gl = g_losses[:4].contiguous() if g_losses is not None else None
+        g_rgb = g_rgb.contiguous() if g_rgb is not None else None
+        g_depth = g_depth.contiguous() if g_depth is not None else None
         L.call("mf_render_loss_bwd", L.ptr(raw), L.ptr(z), L.ptr(target_rgb), L.ptr(target_d), L.ptr(counts), L.ptr(losses),
-               C.byref(cfg), L.ptr(gl), L.ptr(g_rgb.contiguous() if g_rgb is not None else None),
-               L.ptr(g_depth.contiguous() if g_depth is not None else None), L.ptr(d_raw), R, S, st)
+               C.byref(cfg), L.ptr(gl), L.ptr(g_rgb), L.ptr(g_depth), L.ptr(d_raw), R, S, st)
         if g_raw is not None:
             d_raw = d_raw + g_raw
         want_rays = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]

@@ -49,8 +49,14 @@ def fixture_state(fx):
     return {k[2:]: T(v) for k, v in fx.items() if k.startswith("w:")}
 
 
+def _np64(a):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.asarray(a, dtype=np.float64)
+
+
 def rel_err(a, b):
-    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    a, b = _np64(a), _np64(b)
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
 
 

@@ -56,7 +56,8 @@ def test_gen_rays():
     idx = torch.randint(-1, K, (R,), generator=g)
     rd_o, ro_o = osamp.rays_camera_to_world2(dirs, poses, idx)
     ro = torch.empty(R, 3, device="cuda"); rd = torch.empty(R, 3, device="cuda")
-    L.call("mf_gen_rays", L.ptr(dirs.cuda()), L.ptr(poses.cuda()), L.ptr(idx.cuda()), L.ptr(ro), L.ptr(rd), R, K, L.stream())
+    dirs_c, poses_c, idx_c = dirs.cuda(), poses.cuda(), idx.cuda()          # keep the device copies alive across the calls
+    L.call("mf_gen_rays", L.ptr(dirs_c), L.ptr(poses_c), L.ptr(idx_c), L.ptr(ro), L.ptr(rd), R, K, L.stream())
     assert np.array_equal(ro.cpu().numpy(), ro_o.numpy())
     np.testing.assert_allclose(rd.cpu().numpy(), rd_o.numpy(), rtol=1e-6, atol=1e-6)
     po = poses.clone().requires_grad_(True)
@@ -64,7 +65,8 @@ def test_gen_rays():
     go, gd = torch.randn(R, 3, generator=g), torch.randn(R, 3, generator=g)
     (ro2 * go).sum().add((rd2 * gd).sum()).backward()
     dp = torch.zeros(K, 4, 4, device="cuda")
-    L.call("mf_gen_rays_bwd", L.ptr(dirs.cuda()), L.ptr(idx.cuda()), L.ptr(go.cuda()), L.ptr(gd.cuda()), L.ptr(dp), R, K, L.stream())
+    go_c, gd_c = go.cuda(), gd.cuda()
+    L.call("mf_gen_rays_bwd", L.ptr(dirs_c), L.ptr(idx_c), L.ptr(go_c), L.ptr(gd_c), L.ptr(dp), R, K, L.stream())
     assert H.rel_err(dp.cpu(), po.grad) < 1e-4
 
 
@@ -130,12 +132,13 @@ def test_ro_baseline_shape_shards_agree():
     target_d = frame["depth"].reshape(-1).cuda(); rays_d = dirs[rows, cols].contiguous().cuda()
     rot, trans = c2w[:3, :3].contiguous().cuda(), c2w[:3, 3].contiguous().cuda()
     search = torch.full((6,), 0.02, device="cuda")
+    particles_c = particles.cuda()
     field = model._field()
 
     def score(b, n):
         fit = torch.empty(n, device="cuda"); ms = torch.empty(n, device="cuda"); p7 = torch.empty(n, 7, device="cuda")
         scratch = torch.empty(n * (P + 12), device="cuda")
-        L.call("mf_ro_score", L.ptr(particles.cuda()), L.ptr(search), L.ptr(rot), L.ptr(trans), L.ptr(rays_d), L.ptr(target_d),
+        L.call("mf_ro_score", L.ptr(particles_c), L.ptr(search), L.ptr(rot), L.ptr(trans), L.ptr(rays_d), L.ptr(target_d),
                C.byref(field), 0.1, 1000.0, b, n, P, L.ptr(fit), L.ptr(ms), L.ptr(p7), L.ptr(scratch), L.stream())
         return fit, ms, p7
     full = score(0, Cn)
