@@ -75,6 +75,17 @@ int mf_abi_version(void);
 /* Number of SMs of the current device (grid sizing); <0 on error. */
 int mf_device_sm_count(void);
 
+/* Decoder implementation used by the forward field kernels: 0 = tcgen05 tensor cores with a bf16x3 split
+ * (default), 1 = fp32 CUDA cores (numerical reference).  Process-wide; meant for verification. */
+int mf_set_decoder_impl(int impl);
+int mf_get_decoder_impl(void);
+/* 1 if a tensor-core kernel reported an MMA-completion timeout since the last call (clears the flag;
+ * synchronises the device -- diagnostics only). */
+int mf_tc_check_error(void);
+/* Diagnostics: out (128,128) = x (128,K) w (128,K)^T through one tcgen05 layer; K % 16 == 0, K <= 128;
+ * passes = 1 (bf16) or 3 (bf16x3 split). */
+int mf_debug_umma_linear(const float* x, const float* w, float* out, int K, int passes, void* stream);
+
 /* ---- a1: hash-grid encoding (replaces tcnn.Encoding "HashGrid", model/encodings.py:14-25) ---- */
 int mf_hashgrid_meta(int log2_hashmap_size, int n_levels, int n_features, int base_resolution,
                      double per_level_scale, mf_grid_meta* meta_host);

@@ -52,6 +52,10 @@ PROTOTYPES = {
     "mf_last_error": (C.c_char_p, []),
     "mf_abi_version": (_I, []),
     "mf_device_sm_count": (_I, []),
+    "mf_set_decoder_impl": (_I, [_I]),
+    "mf_get_decoder_impl": (_I, []),
+    "mf_tc_check_error": (_I, []),
+    "mf_debug_umma_linear": (_I, [_P, _P, _P, _I, _I, _P]),
     "mf_hashgrid_meta": (_I, [_I, _I, _I, _I, _D, C.POINTER(GridMeta)]),
     "mf_hashgrid_fwd": (_I, [_P, _P, C.POINTER(GridMeta), _P, _P, _L, _P]),
     "mf_hashgrid_bwd": (_I, [_P, _P, _P, C.POINTER(GridMeta), _P, _P, _L, _P]),

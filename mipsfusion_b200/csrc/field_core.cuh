@@ -317,13 +317,12 @@ __device__ __forceinline__ void mlp_forward_tile(const float* __restrict__ prep,
     }
 }
 
-// Coalesced store of the tile's OUT rows to raw (N,10).
-__device__ __forceinline__ void store_raw_tile(const float* sm, float* __restrict__ raw, int64_t tile, int64_t N) {
-    const float* OUT = sm + ROW_OUT * LDA;
-    const int64_t base = tile * TP;
-    const int nv = (int)min((int64_t)TP, N - base);
-    for (int idx = threadIdx.x; idx < nv * MF_RAW_DIM; idx += NT) {
+// Coalesced store of a tile's outputs OUT[c][m] (row length ld, tp points per tile) to raw (N,10).
+__device__ __forceinline__ void store_raw_tile(const float* OUT, int ld, int tp, float* __restrict__ raw, int64_t tile, int64_t N) {
+    const int64_t base = tile * tp;
+    const int nv = (int)min((int64_t)tp, N - base);
+    for (int idx = threadIdx.x; idx < nv * MF_RAW_DIM; idx += blockDim.x) {
         const int m = idx / MF_RAW_DIM, c = idx % MF_RAW_DIM;
-        raw[base * MF_RAW_DIM + idx] = OUT[c * LDA + m];
+        raw[base * MF_RAW_DIM + idx] = OUT[c * ld + m];
     }
 }

@@ -2,13 +2,14 @@
 //   mf_hashgrid_*, mf_freq_*, mf_mlp_*, mf_field_query(_bwd), mf_field_query_rays(_bwd).
 #include "field_bwd.cuh"
 #include "field_launch.cuh"
+#include "field_tc_launch.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Weight re-layout (runs once per optimiser step; 36.6 k floats).
 // ---------------------------------------------------------------------------------------------
 __global__ void mlp_prepare_kernel(const float* __restrict__ mlp, float* __restrict__ prep) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= PREP_SIZE) return;
+    if (i >= PREP_SIMT_SIZE) return;
     float v = 0.f;
     if (i < MF_MLP_PARAMS) {
         v = mlp[i];
@@ -35,7 +36,48 @@ __global__ void mlp_prepare_kernel(const float* __restrict__ mlp, float* __restr
     prep[i] = v;
 }
 
-// (the generic forward kernel template lives in field_launch.cuh)
+// bf16 hi/lo, 128B-swizzled K-major weight image + fp32 head section for the tcgen05 decoder (field_tc.cuh)
+__global__ void mlp_prepare_tc_kernel(const float* __restrict__ mlp, uint8_t* __restrict__ img) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    // one thread per (layer, n, k) weight element: 128 x (64 + 128 + 128)
+    if (t < 128 * 320) {
+        const int n = t / 320, kk = t % 320;
+        float w; int hi_off, lo_off, k;
+        if (kk < 64) {                     // pts_linear.0, slot order
+            k = kk; const int e = tc_e_slot_to_index(k);
+            w = e >= 0 ? mlp[OFF_W1 + n * D_E + e] : 0.f;
+            hi_off = IMG_W1_HI; lo_off = IMG_W1_LO;
+        } else if (kk < 192) {             // pts_linear.2
+            k = kk - 64; w = mlp[OFF_W2 + n * D_H + k];
+            hi_off = IMG_W2_HI; lo_off = IMG_W2_LO;
+        } else {                           // sdf_linear.0 (K = 96, zero padded to 128)
+            k = kk - 192; w = k < D_SDF_IN ? mlp[OFF_WS1 + n * D_SDF_IN + k] : 0.f;
+            hi_off = IMG_W3_HI; lo_off = IMG_W3_LO;
+        }
+        const __nv_bfloat16 h = __float2bfloat16_rn(w);
+        const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+        const uint32_t off = (uint32_t)(k >> 6) * IMG_BLOCK + sw128_offset(n, k & 63);
+        *reinterpret_cast<__nv_bfloat16*>(img + hi_off + off) = h;
+        *reinterpret_cast<__nv_bfloat16*>(img + lo_off + off) = l;
+    } else if (t < 128 * 320 + F_COUNT) {
+        const int j = t - 128 * 320;
+        float v = 0.f;
+        if (j < F_B2) v = mlp[OFF_B1 + j];
+        else if (j < F_BS1) v = mlp[OFF_B2 + (j - F_B2)];
+        else if (j < F_WR_EMB) v = mlp[OFF_BS1 + (j - F_BS1)];
+        else if (j < F_WR_E) { const int c = (j - F_WR_EMB) / 64, k = (j - F_WR_EMB) % 64; v = mlp[OFF_WR + c * D_RGB_IN + k]; }
+        else if (j < F_BR) {
+            const int c = (j - F_WR_E) / 64, e = tc_e_slot_to_index((j - F_WR_E) % 64);
+            v = e >= 0 ? mlp[OFF_WR + c * D_RGB_IN + 64 + e] : 0.f;
+        }
+        else if (j < F_WS2) v = (j - F_BR) < 3 ? mlp[OFF_BR + (j - F_BR)] : 0.f;
+        else if (j < F_BS2) v = mlp[OFF_WS2 + (j - F_WS2)];
+        else v = (j - F_BS2) < 5 ? mlp[OFF_BS2 + (j - F_BS2)] : 0.f;
+        reinterpret_cast<float*>(img + IMG_F32)[j] = v;
+    }
+}
+
+// (the generic forward kernel templates live in field_launch.cuh / field_tc_launch.cuh)
 __global__ void __launch_bounds__(NT, 2) mlp_fwd_kernel(const float* embed, const float* embed_pos, const float* pts,
                                                         const float* __restrict__ prep, float* __restrict__ out, int64_t N) {
     extern __shared__ __align__(16) float sm[];
@@ -45,7 +87,7 @@ __global__ void __launch_bounds__(NT, 2) mlp_fwd_kernel(const float* embed, cons
         __syncthreads();
         mlp_forward_tile<false>(prep, sm, sm + ROW_H1 * LDA);
         __syncthreads();
-        store_raw_tile(sm, out, tile, N);
+        store_raw_tile(sm + ROW_OUT * LDA, LDA, TP, out, tile, N);
         __syncthreads();
     }
 }
@@ -216,6 +258,7 @@ int mf_field_to_dev(const mf_field* f, FieldDev* d) {
         return MF_ERR_UNSUPPORTED;
     }
     d->grid = f->grid; d->prep = f->mlp_prep;
+    d->tc_img = reinterpret_cast<const uint8_t*>(f->mlp_prep + PREP_TC);
     for (int k = 0; k < 3; ++k) { d->na[k] = f->norm_a[k]; d->nb[k] = f->norm_b[k]; }
     d->nf = f->norm_factor;
     d->n_levels = f->meta.n_levels;
@@ -320,7 +363,10 @@ MF_API int64_t mf_mlp_prep_size(void) { return PREP_SIZE; }
 
 MF_API int mf_mlp_prepare(const float* mlp, float* mlp_prep, void* stream) {
     MF_CHECK_ARG(mlp && mlp_prep);
-    mlp_prepare_kernel<<<(PREP_SIZE + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mlp, mlp_prep);
+    mlp_prepare_kernel<<<(PREP_SIMT_SIZE + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mlp, mlp_prep);
+    MF_LAUNCH_CHECK();
+    mlp_prepare_tc_kernel<<<(128 * 320 + F_COUNT + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        mlp, reinterpret_cast<uint8_t*>(mlp_prep + PREP_TC));
     MF_LAUNCH_CHECK();
     return MF_OK;
 }
@@ -383,7 +429,7 @@ MF_API int mf_field_query(const float* pts, const mf_field* field, int normalize
     MF_CHECK_ARG(pts && out);
     FieldDev d; int rc = mf_field_to_dev(field, &d); if (rc) return rc;
     SrcPoints src{pts, normalize};
-    return launch_field_fwd<SrcPoints, EpiRaw, false>(d, src, EpiRaw{out}, N, (cudaStream_t)stream);
+    return launch_field_fwd_auto<SrcPoints, EpiRaw, false>(d, src, EpiRaw{out}, N, (cudaStream_t)stream);
 }
 
 MF_API int mf_field_query_bwd(const float* pts, const mf_field* field, int normalize, const float* d_out, float* grad_grid,
@@ -403,7 +449,7 @@ MF_API int mf_field_query_rays(const float* rays_o, const float* rays_d, const f
     MF_CHECK_ARG(rays_o && rays_d && z && raw);
     FieldDev d; int rc = mf_field_to_dev(field, &d); if (rc) return rc;
     SrcRays src{rays_o, rays_d, z, S};
-    return launch_field_fwd<SrcRays, EpiRaw, false>(d, src, EpiRaw{raw}, R * S, (cudaStream_t)stream);
+    return launch_field_fwd_auto<SrcRays, EpiRaw, false>(d, src, EpiRaw{raw}, R * S, (cudaStream_t)stream);
 }
 
 MF_API int mf_field_query_rays_bwd(const float* rays_o, const float* rays_d, const float* z, const mf_field* field,

@@ -2,6 +2,7 @@
 // Reference: model/Mesher.py:464-528 (geometry), :606-663 (colour); vis/math_helper.py:47-96;
 // helper_functions/geometry_helper.py:93-99 (world -> submap frame).
 #include "field_launch.cuh"
+#include "field_tc_launch.cuh"
 
 constexpr int64_t JQ_CHUNK = 4 << 20;        // points per internal chunk (bounds the compacted index list)
 
@@ -82,15 +83,14 @@ struct SrcJoint {                       // compacted list entry -> world point -
 struct EpiJoint {
     PointSetDev ps; SubmapDev sub; const int* list; int64_t origin; int64_t c_begin;
     const uint8_t* vis; int M, m; const float* max_dist; int color; float* acc; uint8_t* mask_any;
-    __device__ __forceinline__ void store(const float* sm, int64_t tile, int64_t N) const {
+    __device__ __forceinline__ void store(const float* OUT, int ld, int tp, int64_t tile, int64_t N) const {
         const int t = threadIdx.x;
-        const int64_t i = tile * TP + t;
-        if (t >= TP || i >= N) return;
+        const int64_t i = tile * tp + t;
+        if (t >= tp || i >= N) return;
         const int64_t li = c_begin + list[i];                             // index relative to g_begin
         if (vis && !vis[li * M + m]) return;                              // Mesher.py:509-512
         double p[3]; ps.get(origin + list[i], p);
-        const float* OUT = sm + ROW_OUT * LDA;
-        const float ent = fminf(fmaxf(OUT[4 * LDA + t], 0.f), 10000.f);   // np.clip(entropy, 0, 1e4)
+        const float ent = fminf(fmaxf(OUT[4 * ld + t], 0.f), 10000.f);   // np.clip(entropy, 0, 1e4)
         const float d = sub.dist(p);
         const float sigma = max_dist[m] / 3.0f;                            // convert_dist_to_weight, math_helper.py:66-72
         const float k1 = 1.0f / (sigma * 2.50662827463100050f);           // pdf_gauss, vis/math_helper.py:47-51
@@ -100,11 +100,11 @@ struct EpiJoint {
         if (color) {
             float* a = acc + li * 4;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) a[k] = fmaf(w, sigmoidf_(OUT[k * LDA + t]), a[k]);
+            for (int k = 0; k < 3; ++k) a[k] = fmaf(w, sigmoidf_(OUT[k * ld + t]), a[k]);
             a[3] += w;
         } else {
             float* a = acc + li * 2;
-            a[0] = fmaf(w, OUT[3 * LDA + t], a[0]);
+            a[0] = fmaf(w, OUT[3 * ld + t], a[0]);
             a[1] += w;
         }
     }
@@ -180,8 +180,8 @@ MF_API int mf_joint_query_accumulate(const mf_point_set* ps, const mf_submap* su
             MF_LAUNCH_CHECK();
             SrcJoint src{p, sub, list, g_begin + c_begin};
             EpiJoint epi{p, sub, list, g_begin + c_begin, c_begin, vis, M, m, max_dist, color, acc, mask_any};
-            if (color) rc = launch_field_fwd<SrcJoint, EpiJoint, false>(d, src, epi, c_count, st, counter);
-            else rc = launch_field_fwd<SrcJoint, EpiJoint, true>(d, src, epi, c_count, st, counter);
+            if (color) rc = launch_field_fwd_auto<SrcJoint, EpiJoint, false>(d, src, epi, c_count, st, counter);
+            else rc = launch_field_fwd_auto<SrcJoint, EpiJoint, true>(d, src, epi, c_count, st, counter);
             if (rc) return rc;
         }
     }

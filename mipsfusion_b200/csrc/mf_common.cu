@@ -33,3 +33,36 @@ MF_API int mf_device_sm_count(void) {
     MF_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     return n;
 }
+
+// ---- decoder implementation switch + tensor-core error flag ------------------------------------
+static int g_decoder_impl = 0;
+int mf_decoder_impl() { return g_decoder_impl; }
+
+MF_API int mf_set_decoder_impl(int impl) {
+    MF_CHECK_ARG(impl == 0 || impl == 1);
+    g_decoder_impl = impl;
+    return MF_OK;
+}
+MF_API int mf_get_decoder_impl(void) { return g_decoder_impl; }
+
+static int* g_tc_err[64] = {nullptr};
+int* mf_tc_error_flag() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!g_tc_err[dev]) {
+        if (cudaMalloc(&g_tc_err[dev], sizeof(int)) != cudaSuccess) return nullptr;
+        cudaMemset(g_tc_err[dev], 0, sizeof(int));
+    }
+    return g_tc_err[dev];
+}
+
+// Returns 1 if any tensor-core kernel on the current device reported an MMA completion timeout since the
+// last call (and clears the flag).  Synchronises the device: diagnostics only.
+MF_API int mf_tc_check_error(void) {
+    int* p = mf_tc_error_flag();
+    if (!p) return MF_ERR_CUDA;
+    int v = 0;
+    MF_CUDA(cudaMemcpy(&v, p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (v) MF_CUDA(cudaMemset(p, 0, sizeof(int)));
+    return v;
+}

@@ -75,13 +75,16 @@ constexpr int PREP_F3 = PREP_F2 + 128 * 128;      // 96 x 128
 constexpr int PREP_B1 = PREP_F3 + 96 * 128;       // 128 x 64   (KI = 4)
 constexpr int PREP_B2 = PREP_B1 + 128 * 64;       // 128 x 128  (KI = 8)
 constexpr int PREP_B3 = PREP_B2 + 128 * 128;      // 128 x 96   (KI = 6)
-constexpr int PREP_SIZE = PREP_B3 + 128 * 96;
-static_assert(PREP_F1 >= MF_MLP_PARAMS && PREP_F1 % 4 == 0, "alignment");
+constexpr int PREP_SIMT_SIZE = PREP_B3 + 128 * 96;
+constexpr int PREP_TC = PREP_SIMT_SIZE;           // tensor-core weight image (field_tc.cuh), 169,552 bytes
+constexpr int PREP_SIZE = PREP_TC + 42388;
+static_assert(PREP_F1 >= MF_MLP_PARAMS && PREP_F1 % 4 == 0 && PREP_TC % 4 == 0, "alignment");
 
 // Device-side copy of mf_grid_meta + normalisation, passed by value as a kernel parameter.
 struct FieldDev {
     const float* grid;
     const float* prep;
+    const uint8_t* tc_img;        // prep + PREP_TC: bf16 hi/lo weight image of the tcgen05 decoder
     double na[3], nb[3], nf;
     int n_levels;
     float scale[MF_MAX_LEVELS];
@@ -89,6 +92,8 @@ struct FieldDev {
 };
 
 int mf_field_to_dev(const mf_field* f, FieldDev* d);   // validates (16 levels, 2 features)
+int mf_decoder_impl();                                 // 0: tcgen05 tensor cores (default), 1: fp32 CUDA cores
+int* mf_tc_error_flag();                               // device int, set by a kernel whose MMA wait timed out
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -1,6 +1,7 @@
 // RandomOptimizer: particle pose-candidate scoring and the swarm update (a13).
 // Reference: RandomOptimizer.py:54-73 (6D->7D, absolute poses), :81-85,113-131 (fitness), :202-224 (update).
 #include "field_launch.cuh"
+#include "field_tc_launch.cuh"
 
 // pytorch3d.transforms.quaternion_to_matrix (real part first, two_s = 2 / |q|^2)
 __device__ __forceinline__ void quat_to_mat(const float q[4], float m[9]) {
@@ -64,12 +65,12 @@ struct SrcRO {                             // world point of (candidate, pixel):
 
 struct EpiAbsSdf {                         // valid * |sdf * trunc| per (candidate, pixel)
     float* out; const float* depth; int P; float trunc;
-    __device__ __forceinline__ void store(const float* sm, int64_t tile, int64_t N) const {
+    __device__ __forceinline__ void store(const float* OUT, int ld, int tp, int64_t tile, int64_t N) const {
         const int m = threadIdx.x;
-        const int64_t i = tile * TP + m;
-        if (m < TP && i < N) {
+        const int64_t i = tile * tp + m;
+        if (m < tp && i < N) {
             const float valid = depth[i % P] > 0.f ? 1.f : 0.f;
-            out[i] = valid * fabsf(__fmul_rn(sm[(ROW_OUT + 3) * LDA + m], trunc));
+            out[i] = valid * fabsf(__fmul_rn(OUT[3 * ld + m], trunc));
         }
     }
 };
@@ -185,7 +186,7 @@ MF_API int mf_ro_score(const float* particles6, const float* search_size, const 
     MF_LAUNCH_CHECK();
     SrcRO src{Rt, dirs_cam, target_d, P};
     EpiAbsSdf epi{vals, target_d, P, (float)trunc};
-    rc = launch_field_fwd<SrcRO, EpiAbsSdf, true>(d, src, epi, (int64_t)c_count * P, st);
+    rc = launch_field_fwd_auto<SrcRO, EpiAbsSdf, true>(d, src, epi, (int64_t)c_count * P, st);
     if (rc) return rc;
     ro_reduce_kernel<<<(c_count + 7) / 8, 256, 0, st>>>(vals, c_count, P, (float)sdf_weight, fitness, mean_sdf);
     MF_LAUNCH_CHECK();
