@@ -55,6 +55,8 @@ typedef struct {
     const float* mlp_prep;    /* kernel-layout weights written by mf_mlp_prepare */
     double norm_a[3], norm_b[3];
     double norm_factor;       /* training.norm_factor */
+    int32_t decoder_impl;     /* 0: process default (mf_set_decoder_impl), 1: fp32 CUDA cores, 2: tcgen05 tensor cores */
+    int32_t reserved;
     mf_grid_meta meta;
 } mf_field;
 
@@ -85,6 +87,11 @@ int mf_tc_check_error(void);
 /* Diagnostics: out (128,128) = x (128,K) w (128,K)^T through one tcgen05 layer; K % 16 == 0, K <= 128;
  * passes = 1 (bf16) or 3 (bf16x3 split). */
 int mf_debug_umma_linear(const float* x, const float* w, float* out, int K, int passes, void* stream);
+/* Diagnostics: out (128,Kf) = dz (128,128) w (128,Kf)  (dgrad data path: TMEM A, MN-major weight image), Kf in {64,96,128}. */
+int mf_debug_umma_dgrad(const float* dz, const float* w, float* out, int Kf, void* stream);
+/* Diagnostics: out (128,Kf)[n][k] = sum_p dz[p][n] x[p][k] over 128 points (wgrad data path: both operands MN-major
+ * from shared memory, two 64-point half tiles); passes = 1 (dz_hi x_hi) or 2 (+ dz_lo x_hi). */
+int mf_debug_umma_wgrad(const float* dz, const float* x, float* out, int Kf, int passes, void* stream);
 
 /* ---- a1: hash-grid encoding (replaces tcnn.Encoding "HashGrid", model/encodings.py:14-25) ---- */
 int mf_hashgrid_meta(int log2_hashmap_size, int n_levels, int n_features, int base_resolution,

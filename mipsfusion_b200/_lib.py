@@ -27,7 +27,7 @@ class GridMeta(C.Structure):
 
 class Field(C.Structure):
     _fields_ = [("grid", C.c_void_p), ("mlp_prep", C.c_void_p), ("norm_a", C.c_double * 3), ("norm_b", C.c_double * 3),
-                ("norm_factor", C.c_double), ("meta", GridMeta)]
+                ("norm_factor", C.c_double), ("decoder_impl", C.c_int32), ("reserved", C.c_int32), ("meta", GridMeta)]
 
 
 class RenderCfg(C.Structure):
@@ -56,6 +56,8 @@ PROTOTYPES = {
     "mf_get_decoder_impl": (_I, []),
     "mf_tc_check_error": (_I, []),
     "mf_debug_umma_linear": (_I, [_P, _P, _P, _I, _I, _P]),
+    "mf_debug_umma_dgrad": (_I, [_P, _P, _P, _I, _P]),
+    "mf_debug_umma_wgrad": (_I, [_P, _P, _P, _I, _I, _P]),
     "mf_hashgrid_meta": (_I, [_I, _I, _I, _I, _D, C.POINTER(GridMeta)]),
     "mf_hashgrid_fwd": (_I, [_P, _P, C.POINTER(GridMeta), _P, _P, _L, _P]),
     "mf_hashgrid_bwd": (_I, [_P, _P, _P, C.POINTER(GridMeta), _P, _P, _L, _P]),

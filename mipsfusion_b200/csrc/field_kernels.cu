@@ -3,6 +3,7 @@
 #include "field_bwd.cuh"
 #include "field_launch.cuh"
 #include "field_tc_launch.cuh"
+#include "field_tc_bwd.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Weight re-layout (runs once per optimiser step; 36.6 k floats).
@@ -261,6 +262,7 @@ int mf_field_to_dev(const mf_field* f, FieldDev* d) {
     d->tc_img = reinterpret_cast<const uint8_t*>(f->mlp_prep + PREP_TC);
     for (int k = 0; k < 3; ++k) { d->na[k] = f->norm_a[k]; d->nb[k] = f->norm_b[k]; }
     d->nf = f->norm_factor;
+    d->impl = f->decoder_impl == 0 ? mf_decoder_impl() : (f->decoder_impl == 1 ? 1 : 0);
     d->n_levels = f->meta.n_levels;
     for (int l = 0; l < MF_MAX_LEVELS; ++l) {
         d->scale[l] = f->meta.scale[l]; d->res[l] = f->meta.resolution[l]; d->size[l] = f->meta.size[l];
@@ -409,6 +411,22 @@ MF_API int mf_mlp_bwd(const float* embed, const float* embed_pos, const float* p
 template <class Src>
 static int launch_field_bwd(const FieldDev& d, const Src& src, const float* d_raw, float* grad_grid, float* grad_mlp,
                             float* d_pts, float* workspace, int64_t N, cudaStream_t st) {
+    if (d.impl == 0) {                                 // tcgen05 path: 128-point tiles, one CTA per SM
+        const int64_t tiles = (N + TC_TP - 1) / TC_TP;
+        const int64_t cap = mf_sm_count_cached();
+        const int grid = (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
+        if (d_pts) {
+            int rc = set_smem(field_bwd_tc_kernel<Src, true>, SMEM_TC_BWD); if (rc) return rc;
+            field_bwd_tc_kernel<Src, true><<<grid, TC_NT, SMEM_TC_BWD, st>>>(d, src, d_raw, grad_grid, workspace, d_pts, N, mf_tc_error_flag());
+        } else {
+            int rc = set_smem(field_bwd_tc_kernel<Src, false>, SMEM_TC_BWD); if (rc) return rc;
+            field_bwd_tc_kernel<Src, false><<<grid, TC_NT, SMEM_TC_BWD, st>>>(d, src, d_raw, grad_grid, workspace, nullptr, N, mf_tc_error_flag());
+        }
+        MF_LAUNCH_CHECK();
+        reduce_partials_kernel<<<(MF_MLP_PARAMS + 255) / 256, 256, 0, st>>>(workspace, grid, grad_mlp);
+        MF_LAUNCH_CHECK();
+        return MF_OK;
+    }
     const int grid = persistent_grid(N, 1);
     if (d_pts) {
         int rc = set_smem(field_bwd_kernel<Src, true>, SMEM_BWD); if (rc) return rc;

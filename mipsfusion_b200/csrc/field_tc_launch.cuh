@@ -18,6 +18,6 @@ static inline int launch_field_fwd_tc(const FieldDev& d, const Src& src, const E
 template <class Src, class Epi, bool SDF_ONLY>
 static inline int launch_field_fwd_auto(const FieldDev& d, const Src& src, const Epi& epi, int64_t N, cudaStream_t st,
                                         const unsigned int* n_dev = nullptr) {
-    if (mf_decoder_impl() == 0) return launch_field_fwd_tc<Src, Epi, SDF_ONLY>(d, src, epi, N, st, n_dev);
+    if (d.impl == 0) return launch_field_fwd_tc<Src, Epi, SDF_ONLY>(d, src, epi, N, st, n_dev);
     return launch_field_fwd<Src, Epi, SDF_ONLY>(d, src, epi, N, st, n_dev);
 }

@@ -86,6 +86,7 @@ struct FieldDev {
     const float* prep;
     const uint8_t* tc_img;        // prep + PREP_TC: bf16 hi/lo weight image of the tcgen05 decoder
     double na[3], nb[3], nf;
+    int impl;                     // resolved decoder implementation: 0 tcgen05, 1 fp32 CUDA cores
     int n_levels;
     float scale[MF_MAX_LEVELS];
     uint32_t res[MF_MAX_LEVELS], size[MF_MAX_LEVELS], offset[MF_MAX_LEVELS], hashed[MF_MAX_LEVELS];

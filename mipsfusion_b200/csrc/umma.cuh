@@ -109,6 +109,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -134,6 +149,52 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
     hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);   // element 2c in the low half
     lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+}
+
+}  // namespace umma
+
+// ---------------------------------------------------------------------------------------------
+// Row-major bf16 tiles in shared memory, [row][feature] with 64-feature (128-byte) blocks and the
+// 128-byte swizzle.  The same bytes serve as
+//   * a K-major operand  (rows = M/N index, features = K)            -- forward / dgrad style, and
+//   * an MN-major operand (rows = K index,  features = M/N index)    -- wgrad style (contraction over rows).
+// ---------------------------------------------------------------------------------------------
+namespace umma {
+
+// Byte offset of (row, feature) in a tile whose 64-feature blocks are `block_bytes` apart
+// (block_bytes = rows * 128).
+__device__ __forceinline__ uint32_t tile_offset(int row, int feat, uint32_t block_bytes) {
+    return (uint32_t)(feat >> 6) * block_bytes + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128) +
+           (uint32_t)(((((feat & 63) >> 3) ^ (row & 7)) & 7) << 4) + (uint32_t)(feat & 7) * 2;
+}
+
+// Thread-per-row store of 32 consecutive features [32 q, 32 q + 32) given as 16 packed bf16 pairs.
+__device__ __forceinline__ void store_row32(uint8_t* tile, int row, int q, const uint32_t (&pk)[16], uint32_t block_bytes) {
+    uint8_t* base = tile + (uint32_t)(q >> 1) * block_bytes + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int chunk = ((q & 1) * 4 + c) ^ (row & 7);
+        *reinterpret_cast<uint4*>(base + (chunk << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+    }
+}
+
+// Thread-per-row store of 16 consecutive features [16 s, 16 s + 16) given as 8 packed bf16 pairs (s < 4: one block).
+__device__ __forceinline__ void store_row16(uint8_t* tile, int row, int s, const uint32_t (&pk)[8]) {
+    uint8_t* base = tile + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int chunk = (s * 2 + c) ^ (row & 7);
+        *reinterpret_cast<uint4*>(base + (chunk << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+    }
+}
+
+// MN-major descriptor of such a tile: start at K-row `row0` (multiple of 8).
+__device__ __forceinline__ uint64_t desc_mn(const uint8_t* tile, int row0, uint32_t block_bytes) {
+    return smem_desc_sw128(smem_u32(tile) + (uint32_t)row0 * 128u, block_bytes, 1024);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
 }
 
 }  // namespace umma

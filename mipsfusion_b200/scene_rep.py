@@ -31,7 +31,9 @@ class _FieldQueryFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pts, normalize, model, grid, *mlp_params):
-        field = model._field()
+        # gradients w.r.t. the points (pose path) amplify forward rounding, so that route uses the fp32 decoder
+        ctx.impl = 1 if pts.requires_grad else 0
+        field = model._field(impl=ctx.impl)
         N = pts.shape[0]
         out = torch.empty(N, L.MF_RAW_DIM, device=pts.device, dtype=torch.float32)
         L.call("mf_field_query", L.ptr(pts), C.byref(field), int(normalize), L.ptr(out), N, L.stream())
@@ -45,7 +47,7 @@ class _FieldQueryFn(torch.autograd.Function):
     def backward(ctx, d_out):
         pts, grid = ctx.saved_tensors
         model = ctx.model
-        field = model._field(ctx.keep)
+        field = model._field(ctx.keep, impl=ctx.impl)
         N = pts.shape[0]
         g_grid = torch.zeros_like(grid)
         g_mlp = torch.zeros(L.MF_MLP_PARAMS, device=pts.device, dtype=torch.float32)
@@ -76,7 +78,10 @@ class _RenderFn(torch.autograd.Function):
         R = rays_o.shape[0]
         cfg, lins = model._render_cfg(target_d is not None, emd_w, dev)
         S = cfg.n_samples_d + cfg.n_range_d
-        field = model._field()
+        # pose gradients (d loss / d rays) are ill-conditioned w.r.t. forward rounding (loss residuals cancel, the
+        # frequency encoding multiplies by up to 2^7 pi): that route runs the fp32 decoder end to end
+        ctx.impl = 1 if (rays_o.requires_grad or rays_d.requires_grad) else 0
+        field = model._field(impl=ctx.impl)
         st = L.stream()
         z = torch.empty(R, S, device=dev, dtype=torch.float32)
         counts = torch.empty(2, device=dev, dtype=torch.int64)
@@ -105,7 +110,7 @@ class _RenderFn(torch.autograd.Function):
         model, cfg, S = ctx.model, ctx.cfg, ctx.S
         dev, R = rays_o.device, rays_o.shape[0]
         st = L.stream()
-        field = model._field(ctx.keep)
+        field = model._field(ctx.keep, impl=ctx.impl)
         d_raw = torch.empty_like(raw)
         gl = g_losses[:4].contiguous() if g_losses is not None else None
         g_rgb = g_rgb.contiguous() if g_rgb is not None else None
@@ -179,8 +184,8 @@ class JointEncoding(nn.Module):
             self.__dict__["_norm_cache"] = cache
         return cache[1], cache[2]
 
-    def _field(self, keep=None):
-        """mf_field descriptor of the current weights."""
+    def _field(self, keep=None, impl=0):
+        """mf_field descriptor of the current weights (impl: 0 process default, 1 fp32 CUDA cores, 2 tcgen05)."""
         if self.config["pos"]["enc"].lower().find("freq") < 0 or self.config["pos"]["n_bins"] != 8:
             raise L.MipsFusionB200Error("fused field kernels are built for pos.enc=Frequency, n_bins=8")
         grid = self.embed_fn.params
@@ -193,6 +198,7 @@ class JointEncoding(nn.Module):
         for k in range(3):
             f.norm_a[k], f.norm_b[k] = a[k], b[k]
         f.norm_factor = float(self.config["training"]["norm_factor"])
+        f.decoder_impl = int(impl)
         f.meta = self.embed_fn.meta
         f._keepalive = (grid, prep)
         return f

@@ -48,5 +48,56 @@ def main():
         print("   row 9 nonzeros:", o[9].nonzero().flatten().tolist()[:16], " expected:", ref[9].nonzero().flatten().tolist()[:16])
 
 
+def probes2():
+    g = torch.Generator().manual_seed(1)
+    for Kf in (64, 96, 128):
+        dz = torch.randn(128, 128, generator=g); w = torch.randn(128, Kf, generator=g)
+        dzc, wc = dz.cuda(), w.cuda()
+        out = torch.full((128, Kf), float("nan"), device="cuda")
+        L.call("mf_debug_umma_dgrad", L.ptr(dzc), L.ptr(wc), L.ptr(out), Kf, L.stream()); torch.cuda.synchronize()
+        ref = dz.double() @ w.double()
+        o = out.cpu()
+        print(f"dgrad Kf={Kf:3d}: rel err {(o.double() - ref).abs().max().item() / ref.abs().max().item():.3e} nan={int(torch.isnan(o).sum())} timeout={L.lib().mf_tc_check_error()}")
+        x = torch.randn(128, Kf, generator=g); xc = x.cuda()
+        for passes in (1, 2):
+            out = torch.full((128, Kf), float("nan"), device="cuda")
+            L.call("mf_debug_umma_wgrad", L.ptr(dzc), L.ptr(xc), L.ptr(out), Kf, passes, L.stream()); torch.cuda.synchronize()
+            ref = dz.double().T @ x.double()
+            o = out.cpu()
+            print(f"wgrad Kf={Kf:3d} passes={passes}: rel err {(o.double() - ref).abs().max().item() / ref.abs().max().item():.3e} nan={int(torch.isnan(o).sum())} timeout={L.lib().mf_tc_check_error()}")
+    # structured probe for wgrad layout: dz = one-hot rows, x = one-hot rows
+    Kf = 128
+    dz = torch.zeros(128, 128); x = torch.zeros(128, Kf)
+    for p in range(128):
+        dz[p, (3 * p) % 128] = 1.0; x[p, (5 * p + 1) % Kf] = 1.0 + p / 256.0
+    out = torch.zeros(128, Kf, device="cuda")
+    dzc, xc = dz.cuda(), x.cuda()
+    L.call("mf_debug_umma_wgrad", L.ptr(dzc), L.ptr(xc), L.ptr(out), Kf, 1, L.stream()); torch.cuda.synchronize()
+    ref = dz.T @ x
+    bad = (out.cpu() - ref).abs() > 1e-2
+    print("wgrad probe mismatches:", int(bad.sum()))
+    if bad.any():
+        o = out.cpu()
+        for r, c in bad.nonzero()[:8].tolist():
+            print(f"   out[{r},{c}] = {o[r, c]:.4f} expected {ref[r, c]:.4f}")
+    dz = torch.zeros(128, 128); w = torch.zeros(128, 128)
+    for p in range(128):
+        dz[p, (3 * p) % 128] = 1.0
+    for n in range(128):
+        w[n, (7 * n + 2) % 128] = 1.0 + n / 256.0
+    out = torch.zeros(128, 128, device="cuda")
+    dzc, wc = dz.cuda(), w.cuda()
+    L.call("mf_debug_umma_dgrad", L.ptr(dzc), L.ptr(wc), L.ptr(out), 128, L.stream()); torch.cuda.synchronize()
+    ref = dz @ w
+    bad = (out.cpu() - ref).abs() > 1e-2
+    print("dgrad probe mismatches:", int(bad.sum()))
+    if bad.any():
+        o = out.cpu()
+        for r, c in bad.nonzero()[:8].tolist():
+            print(f"   out[{r},{c}] = {o[r, c]:.4f} expected {ref[r, c]:.4f}")
+        print("   row 1 nonzeros:", o[1].nonzero().flatten().tolist()[:8], "expected", ref[1].nonzero().flatten().tolist()[:8])
+
+
 if __name__ == "__main__":
     main()
+    probes2()
