@@ -93,6 +93,9 @@ int mf_debug_umma_dgrad(const float* dz, const float* w, float* out, int Kf, voi
  * from shared memory, two 64-point half tiles); passes = 1 (dz_hi x_hi) or 2 (+ dz_lo x_hi). */
 int mf_debug_umma_wgrad(const float* dz, const float* x, float* out, int Kf, int passes, void* stream);
 
+/* Diagnostics: switch the in-kernel clock stamps of the tensor-core backward on/off and read the last ones. */
+int mf_debug_profile(int on, long long* out_host);
+
 /* ---- a1: hash-grid encoding (replaces tcnn.Encoding "HashGrid", model/encodings.py:14-25) ---- */
 int mf_hashgrid_meta(int log2_hashmap_size, int n_levels, int n_features, int base_resolution,
                      double per_level_scale, mf_grid_meta* meta_host);

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "mf_debug_umma_linear": (_I, [_P, _P, _P, _I, _I, _P]),
     "mf_debug_umma_dgrad": (_I, [_P, _P, _P, _I, _P]),
     "mf_debug_umma_wgrad": (_I, [_P, _P, _P, _I, _I, _P]),
+    "mf_debug_profile": (_I, [_I, _P]),
     "mf_hashgrid_meta": (_I, [_I, _I, _I, _I, _D, C.POINTER(GridMeta)]),
     "mf_hashgrid_fwd": (_I, [_P, _P, C.POINTER(GridMeta), _P, _P, _L, _P]),
     "mf_hashgrid_bwd": (_I, [_P, _P, _P, C.POINTER(GridMeta), _P, _P, _L, _P]),

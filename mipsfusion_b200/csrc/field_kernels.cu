@@ -154,11 +154,18 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const float* embed, cons
 }
 
 // grad_mlp[i] += sum over CTAs of part[cta][i]  (fixed order -> deterministic)
-__global__ void reduce_partials_kernel(const float* __restrict__ part, int n_cta, float* __restrict__ grad_mlp) {
+// transposed != 0: the three 128-row weight matrices are stored [in][out] inside each partial (tensor-core path)
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int n_cta, float* __restrict__ grad_mlp, int transposed) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= MF_MLP_PARAMS) return;
+    int src = i;
+    if (transposed) {
+        if (i < OFF_B1) { const int n = i / D_E, k = i % D_E; src = OFF_W1 + k * D_H + n; }
+        else if (i >= OFF_W2 && i < OFF_B2) { const int r = i - OFF_W2; src = OFF_W2 + (r % D_H) * D_H + r / D_H; }
+        else if (i >= OFF_WS1 && i < OFF_BS1) { const int r = i - OFF_WS1; src = OFF_WS1 + (r % D_SDF_IN) * D_H + r / D_SDF_IN; }
+    }
     float s = 0.f;
-    for (int c = 0; c < n_cta; ++c) s += part[(size_t)c * MF_MLP_PARAMS + i];
+    for (int c = 0; c < n_cta; ++c) s += part[(size_t)c * MF_MLP_PARAMS + src];
     grad_mlp[i] += s;
 }
 
@@ -403,7 +410,7 @@ MF_API int mf_mlp_bwd(const float* embed, const float* embed_pos, const float* p
         mlp_bwd_kernel<false><<<grid, NT, SMEM_BWD, st>>>(embed, embed_pos, pts, mlp_prep, d_out, workspace, d_embed, nullptr, nullptr, N);
     }
     MF_LAUNCH_CHECK();
-    reduce_partials_kernel<<<(MF_MLP_PARAMS + 255) / 256, 256, 0, st>>>(workspace, grid, grad_mlp);
+    reduce_partials_kernel<<<(MF_MLP_PARAMS + 255) / 256, 256, 0, st>>>(workspace, grid, grad_mlp, 0);
     MF_LAUNCH_CHECK();
     return MF_OK;
 }
@@ -417,13 +424,13 @@ static int launch_field_bwd(const FieldDev& d, const Src& src, const float* d_ra
         const int grid = (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
         if (d_pts) {
             int rc = set_smem(field_bwd_tc_kernel<Src, true>, SMEM_TC_BWD); if (rc) return rc;
-            field_bwd_tc_kernel<Src, true><<<grid, TC_NT, SMEM_TC_BWD, st>>>(d, src, d_raw, grad_grid, workspace, d_pts, N, mf_tc_error_flag());
+            field_bwd_tc_kernel<Src, true><<<grid, TC_NT, SMEM_TC_BWD, st>>>(d, src, d_raw, grad_grid, workspace, d_pts, N, mf_tc_error_flag(), mf_tc_profile_buffer());
         } else {
             int rc = set_smem(field_bwd_tc_kernel<Src, false>, SMEM_TC_BWD); if (rc) return rc;
-            field_bwd_tc_kernel<Src, false><<<grid, TC_NT, SMEM_TC_BWD, st>>>(d, src, d_raw, grad_grid, workspace, nullptr, N, mf_tc_error_flag());
+            field_bwd_tc_kernel<Src, false><<<grid, TC_NT, SMEM_TC_BWD, st>>>(d, src, d_raw, grad_grid, workspace, nullptr, N, mf_tc_error_flag(), mf_tc_profile_buffer());
         }
         MF_LAUNCH_CHECK();
-        reduce_partials_kernel<<<(MF_MLP_PARAMS + 255) / 256, 256, 0, st>>>(workspace, grid, grad_mlp);
+        reduce_partials_kernel<<<(MF_MLP_PARAMS + 255) / 256, 256, 0, st>>>(workspace, grid, grad_mlp, 1);
         MF_LAUNCH_CHECK();
         return MF_OK;
     }
@@ -436,7 +443,7 @@ static int launch_field_bwd(const FieldDev& d, const Src& src, const float* d_ra
         field_bwd_kernel<Src, false><<<grid, NT, SMEM_BWD, st>>>(d, src, d_raw, grad_grid, workspace, nullptr, N);
     }
     MF_LAUNCH_CHECK();
-    reduce_partials_kernel<<<(MF_MLP_PARAMS + 255) / 256, 256, 0, st>>>(workspace, grid, grad_mlp);
+    reduce_partials_kernel<<<(MF_MLP_PARAMS + 255) / 256, 256, 0, st>>>(workspace, grid, grad_mlp, 0);
     MF_LAUNCH_CHECK();
     return MF_OK;
 }

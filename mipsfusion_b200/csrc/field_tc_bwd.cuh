@@ -20,7 +20,10 @@ constexpr int BS_R2 = 163840;                          // 32 KB: wgrad X tiles (
 constexpr int BS_F32 = 196608;                         // fp32 section of the image
 constexpr int BS_PART = BS_F32 + ((F_COUNT * 4 + 127) / 128) * 128;
 constexpr int BS_PART_ROWS = 32;                       // 20 logit partial rows + 12 dx partial rows
-constexpr int BS_BAR = BS_PART + BS_PART_ROWS * TC_LD * 4;
+constexpr int BS_SACC = BS_PART + BS_PART_ROWS * TC_LD * 4;   // fp32 accumulators of the narrow heads and biases
+constexpr int SA_W4 = 0, SA_WR = 640, SA_B1 = 640 + 345, SA_B2 = SA_B1 + 128, SA_BS1 = SA_B2 + 128, SA_B4 = SA_BS1 + 128, SA_BR = SA_B4 + 5;
+constexpr int SA_COUNT = SA_BR + 3;
+constexpr int BS_BAR = BS_SACC + ((SA_COUNT * 4 + 127) / 128) * 128;
 constexpr int BS_BYTES = BS_BAR + 32;
 constexpr size_t SMEM_TC_BWD = BS_BYTES + 1024;
 static_assert(SMEM_TC_BWD <= 227 * 1024, "shared memory budget");
@@ -34,7 +37,7 @@ constexpr int TB_G_HI = TB_OP2_HI + 32, TB_G_LO = TB_OP2_LO + 32;   // grid feat
 
 struct TbCtx {
     uint8_t *w2, *w3, *r1, *r2;
-    const float* fw; float* part; uint64_t* bar; uint32_t* tmem_ptr;
+    const float* fw; float* part; float* sacc; uint64_t* bar; uint32_t* tmem_ptr;
     uint32_t tmem_base, lane_base, phase;
     bool ok;
 };
@@ -47,7 +50,8 @@ __device__ __forceinline__ void tb_copy(uint8_t* dst, const uint8_t* __restrict_
 __device__ __forceinline__ void tb_setup(TbCtx& c, uint8_t* smem_raw, const uint8_t* __restrict__ img) {
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     c.w2 = base + BS_W2; c.w3 = base + BS_W3; c.r1 = base + BS_R1; c.r2 = base + BS_R2;
-    c.fw = (const float*)(base + BS_F32); c.part = (float*)(base + BS_PART);
+    c.fw = (const float*)(base + BS_F32); c.part = (float*)(base + BS_PART); c.sacc = (float*)(base + BS_SACC);
+    for (int i = threadIdx.x; i < SA_COUNT; i += blockDim.x) c.sacc[i] = 0.f;
     c.bar = (uint64_t*)(base + BS_BAR); c.tmem_ptr = (uint32_t*)(base + BS_BAR + 8);
     tb_copy(c.w2, img + IMG_W2_HI, 4 * IMG_BLOCK);
     tb_copy(c.w3, img + IMG_W3_HI, 4 * IMG_BLOCK);
@@ -154,6 +158,16 @@ __device__ __forceinline__ float rs16(float (&v)[16], int lane) {
     return v[0];
 }
 
+// the 16 layer-1 input slots owned by thread q of a point (12 frequency features, xyz for q = 0, zero padding)
+__device__ __forceinline__ void tb_e_slots(const float (&x)[3], int q, float (&e)[16]) {
+#pragma unroll
+    for (int jj = 0; jj < 12; ++jj) {
+        const int j = q * 12 + jj, d = j >> 4, k = (j & 15) >> 1, s = j & 1;
+        e[jj] = sinf(freq_arg(x[d], k, s));
+    }
+    e[12] = q == 0 ? x[0] : 0.f; e[13] = q == 0 ? x[1] : 0.f; e[14] = q == 0 ? x[2] : 0.f; e[15] = 0.f;
+}
+
 __device__ __forceinline__ void tb_load32(const TbCtx& c, int col, float (&v)[32]) {
     uint32_t r[32];
     umma::tmem_ld32(c.lane_base + (uint32_t)col, r);
@@ -174,32 +188,42 @@ __device__ __forceinline__ void tb_store_op32(const TbCtx& c, int hi_col, int lo
 // wgrad of one 128-wide layer.  z: this thread's 32 gradient values (features [32q,32q+32) of point p).
 // load_x(hi, lo) fills the packed bf16 pairs of this thread's slice of the activation operand (or returns false
 // when the thread has no slice).  X has n_x features (64, 96 or 128).  The result D[n][k] is added to gW, whose
-// element (n, k) lives at gW[n * ldw + kmap(k)] (kmap(k) < 0: skip).
+// element (n, k) lives at gW[kmap(k) * 128 + n] (transposed, so that a warp's reductions coalesce; kmap(k) < 0: skip;
+// reduce_partials_kernel restores the (out, in) layout).
 template <class LoadX, class KMap>
 __device__ __forceinline__ void tb_wgrad_layer(TbCtx& c, int p, int q, const float (&z)[32], LoadX load_x, int n_x,
                                                float* __restrict__ gW, int ldw, KMap kmap) {
     uint8_t *z_hi = c.r1, *z_lo = c.r1 + 2 * HALF_BLK, *x_hi = c.r2, *x_lo = c.r2 + 2 * HALF_BLK;
-    uint32_t zh[16], zl[16], xh[16], xl[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) umma::split2(z[2 * i], z[2 * i + 1], zh[i], zl[i]);
-    const bool has_x = load_x(xh, xl);
     for (int half = 0; half < 2; ++half) {
-        if ((p >> 6) == half) {
+        if ((p >> 6) == half) {                          // warp-uniform; packed operands are transient registers
             const int row = p & 63;
-            umma::store_row32(z_hi, row, q, zh, HALF_BLK);
-            umma::store_row32(z_lo, row, q, zl, HALF_BLK);
-            if (has_x) { umma::store_row32(x_hi, row, q, xh, HALF_BLK); umma::store_row32(x_lo, row, q, xl, HALF_BLK); }
+            {
+                uint32_t zh[16], zl[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) umma::split2(z[2 * i], z[2 * i + 1], zh[i], zl[i]);
+                umma::store_row32(z_hi, row, q, zh, HALF_BLK);
+                umma::store_row32(z_lo, row, q, zl, HALF_BLK);
+            }
+            {
+                uint32_t xh[16], xl[16];
+                if (load_x(xh, xl)) { umma::store_row32(x_hi, row, q, xh, HALF_BLK); umma::store_row32(x_lo, row, q, xl, HALF_BLK); }
+            }
         }
         tb_round(c, [&]() { tb_issue_wgrad(c, n_x, half == 0); });
     }
-    // read-out: thread (n = p, q) owns D[n][32q .. 32q+32)
+    // read-out: thread (n = p, q) owns D[n][32q .. 32q+32); added to the CTA-private partial with reductions
+    // (fire-and-forget, no load latency)
     if (32 * q < n_x) {
-        float d[32];
-        tb_load32(c, TB_D + 32 * q, d);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const int k = kmap(32 * q + i);
-            if (k >= 0) gW[p * ldw + k] += d[i];
+        for (int c0 = 0; c0 < 32; c0 += 8) {
+            uint32_t r[8];
+            umma::tmem_ld8(c.lane_base + (uint32_t)(TB_D + 32 * q + c0), r);
+            umma::wait_ld();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = kmap(32 * q + c0 + i);
+                if (k >= 0) atomicAdd(&gW[k * D_H + p], __uint_as_float(r[i]));   // [k][n]: lanes (n) are contiguous
+            }
         }
     }
 }
@@ -210,53 +234,48 @@ __device__ __forceinline__ void tb_wgrad_layer(TbCtx& c, int p, int q, const flo
 template <class Src, bool WANT_DX>
 __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src src, const float* __restrict__ d_raw,
                                                                 float* __restrict__ grad_grid, float* __restrict__ part,
-                                                                float* __restrict__ d_pts, int64_t N, int* __restrict__ err) {
+                                                                float* __restrict__ d_pts, int64_t N, int* __restrict__ err,
+                                                                long long* __restrict__ prof) {
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x, p = tid & (TC_TP - 1), q = tid >> 7, lane = tid & 31;
+#define TB_MARK(k) do { if (prof && tid == 0 && blockIdx.x == 0 && tile == (int64_t)gridDim.x) prof[k] = clock64(); } while (0)
     float* gpart = part + (size_t)blockIdx.x * MF_MLP_PARAMS;
     for (int i = tid; i < MF_MLP_PARAMS; i += TC_NT) gpart[i] = 0.f;
     TbCtx c;
     tb_setup(c, smem_raw, f.tc_img);
     const float2* grid2 = reinterpret_cast<const float2*>(f.grid);
-    // per-thread accumulators of the narrow heads / biases (summed over this CTA's tiles)
-    float aW4[N_CLASS] = {0.f, 0.f, 0.f, 0.f, 0.f}, aWrEmb[3] = {0.f, 0.f, 0.f}, aWrE[3] = {0.f, 0.f, 0.f};
-    float aB4[N_CLASS] = {0.f, 0.f, 0.f, 0.f, 0.f}, aBr[3] = {0.f, 0.f, 0.f};
-    float aB1 = 0.f, aB2 = 0.f, aBs1 = 0.f;
 
     const int64_t n_tiles = (N + TC_TP - 1) / TC_TP;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t i = tile * TC_TP + p;
         const bool valid = i < N;
+        TB_MARK(0);
         // ---- W1 image into region 1 (it doubles as the wgrad dZ tile later in the tile) ----
         tb_copy(c.r1, f.tc_img + IMG_W1_HI, 2 * IMG_BLOCK);
-        // ---- upstream gradient of this point ----
-        float g[MF_RAW_DIM];
+        // ---- upstream gradient of the colour outputs of this point (the sdf-head part is loaded at the heads) ----
+        float g[3];
 #pragma unroll
-        for (int k = 0; k < MF_RAW_DIM; ++k) g[k] = valid ? d_raw[i * MF_RAW_DIM + k] : 0.f;
+        for (int k = 0; k < 3; ++k) g[k] = valid ? d_raw[i * MF_RAW_DIM + k] : 0.f;
         // ---- encode ----
         float x[3] = {0.f, 0.f, 0.f};
         if (valid) src.point(i, f, x);
-        float e[16];
-#pragma unroll
-        for (int jj = 0; jj < 12; ++jj) {
-            const int j = q * 12 + jj, d = j >> 4, k = (j & 15) >> 1, s = j & 1;
-            e[jj] = sinf(freq_arg(x[d], k, s));
-        }
-        e[12] = q == 0 ? x[0] : 0.f; e[13] = q == 0 ? x[1] : 0.f; e[14] = q == 0 ? x[2] : 0.f; e[15] = 0.f;
         {
+            float e[16];
+            tb_e_slots(x, q, e);
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) umma::split2(e[2 * t], e[2 * t + 1], hi[t], lo[t]);
             umma::tmem_st8(c.lane_base + TB_OP1_HI + 8 * q, hi);
             umma::tmem_st8(c.lane_base + TB_OP1_LO + 8 * q, lo);
-        }
-        {   // colour head, e part: dWr[c][64 + e_index(slot)] += dRGB[c] e[slot]
-#pragma unroll
+            // colour head, e part: dWr[c][64 + e_index(slot)] += dRGB[c] e[slot]
+#pragma unroll 1
             for (int ch = 0; ch < 3; ++ch) {
                 float t[16];
 #pragma unroll
                 for (int s = 0; s < 16; ++s) t[s] = g[ch] * e[s];
-                aWrE[ch] += rs16(t, lane);
+                const float r = rs16(t, lane);
+                const int ei = tc_e_slot_to_index(16 * q + (lane & 15));
+                if (lane < 16 && ei >= 0) atomicAdd(&c.sacc[SA_WR + ch * D_RGB_IN + 64 + ei], r);
             }
         }
         {
@@ -273,6 +292,7 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
             umma::tmem_st4(c.lane_base + TB_G_HI + 4 * q, hi);
             umma::tmem_st4(c.lane_base + TB_G_LO + 4 * q, lo);
         }
+        TB_MARK(1);
         float v[32];
         uint32_t mask1 = 0, mask3 = 0;
         // ---- forward layer 1 ----
@@ -284,6 +304,7 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
             mask1 |= (v[k] > 0.f ? 1u : 0u) << k;
         }
         tb_store_op32(c, TB_OP1_HI, TB_OP1_LO, q, v);                        // H1 stays in operand 1 until wgrad of layer 2
+        TB_MARK(2);
         // ---- forward layer 2 ----
         tb_round(c, [&]() { tb_issue_fwd(c, c.w2, c.w2 + 2 * IMG_BLOCK, 8, [](int ks, bool lo) { return (lo ? TB_OP1_LO : TB_OP1_HI) + 8 * ks; }); });
         tb_load32(c, TB_D + 32 * q, v);
@@ -292,14 +313,15 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
         if (q < 2) {
             tb_store_op32(c, TB_OP2_HI, TB_OP2_LO, q, v);                    // sdf_emb
         } else {                                                             // colour head, rgb_emb part
-#pragma unroll
+#pragma unroll 1
             for (int ch = 0; ch < 3; ++ch) {
                 float t[32];
 #pragma unroll
                 for (int k = 0; k < 32; ++k) t[k] = g[ch] * v[k];
-                aWrEmb[ch] += rs32(t, lane);
+                atomicAdd(&c.sacc[SA_WR + ch * D_RGB_IN + 32 * (q - 2) + lane], rs32(t, lane));
             }
         }
+        TB_MARK(3);
         // ---- forward layer 3 ----
         tb_round(c, [&]() {
             tb_issue_fwd(c, c.w3, c.w3 + 2 * IMG_BLOCK, 6, [](int ks, bool lo) {
@@ -320,10 +342,14 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
 #pragma unroll
             for (int ch = 0; ch < N_CLASS; ++ch) c.part[(q * 5 + ch) * TC_LD + p] = s[ch];
         }
+        TB_MARK(4);
         __syncthreads();
         // ---- heads: softmax forward + backward (all four threads of a point, redundantly) ----
         float dz4[N_CLASS];
         {
+            float gs[7];                                   // d loss / d (sdf, entropy, prob[5])
+#pragma unroll
+            for (int k = 0; k < 7; ++k) gs[k] = valid ? d_raw[i * MF_RAW_DIM + 3 + k] : 0.f;
             float zl[N_CLASS], pr[N_CLASS], dp[N_CLASS];
             float mx = -INFINITY, se = 0.f, dot = 0.f;
 #pragma unroll
@@ -337,24 +363,24 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
             for (int ch = 0; ch < N_CLASS; ++ch) {
                 pr[ch] = pr[ch] / se;
                 const float qq = pr[ch] + 1e-5f;
-                dp[ch] = g[5 + ch] + g[3] * (0.5f * (float)ch) - g[4] * (log2f(qq) + pr[ch] / (qq * 0.6931471805599453f));
+                dp[ch] = gs[2 + ch] + gs[0] * (0.5f * (float)ch) - gs[1] * (log2f(qq) + pr[ch] / (qq * 0.6931471805599453f));
                 dot = fmaf(pr[ch], dp[ch], dot);
             }
 #pragma unroll
             for (int ch = 0; ch < N_CLASS; ++ch) dz4[ch] = pr[ch] * (dp[ch] - dot);
         }
         // sdf_linear.2 weight gradient: dW4[c][32q + l] += sum_p dz4[c] h3[l]; biases from the q == 0 warps
-#pragma unroll
+#pragma unroll 1
         for (int ch = 0; ch < N_CLASS; ++ch) {
             float t[32];
 #pragma unroll
             for (int k = 0; k < 32; ++k) t[k] = dz4[ch] * v[k];
-            aW4[ch] += rs32(t, lane);
-            if (q == 0) aB4[ch] += warp_sum(dz4[ch]);
+            atomicAdd(&c.sacc[SA_W4 + ch * D_H + 32 * q + lane], rs32(t, lane));
+            if (q == 0) { const float b = warp_sum(dz4[ch]); if (lane == 0) atomicAdd(&c.sacc[SA_B4 + ch], b); }
         }
         if (q == 0) {
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) aBr[ch] += warp_sum(g[ch]);
+            for (int ch = 0; ch < 3; ++ch) { const float b = warp_sum(g[ch]); if (lane == 0) atomicAdd(&c.sacc[SA_BR + ch], b); }
         }
         // dZ3 = (Ws2^T dz4) * relu'(h3)
         {
@@ -370,7 +396,8 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
         { float t[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) t[k] = v[k];
-          aBs1 += rs32(t, lane); }
+          atomicAdd(&c.sacc[SA_BS1 + 32 * q + lane], rs32(t, lane)); }
+        TB_MARK(5);
         // ---- layer 3: wgrad (X = [sdf_emb (operand 2), grid features]), then dgrad ----
         tb_wgrad_layer(c, p, q, v,
             [&](uint32_t (&xh)[16], uint32_t (&xl)[16]) {
@@ -380,6 +407,7 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
                 return q < 3;
             },
             D_SDF_IN, gpart + OFF_WS1, D_SDF_IN, [](int k) { return k < D_SDF_IN ? k : -1; });
+        TB_MARK(6);
         tb_store_op32(c, TB_OP2_HI, TB_OP2_LO, q, v);                        // dZ3 (overwrites sdf_emb + grid features)
         tb_round(c, [&]() { tb_issue_dgrad(c, c.w3, c.w3 + 2 * IMG_BLOCK, D_SDF_IN); });
         // d grid features: D columns [64 + 8q, 64 + 8q + 8) -> scatter into the table (+ dL/dx through the grid)
@@ -395,6 +423,7 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
                                             level_info(f, q * 4 + ll), dx);
             }
         }
+        TB_MARK(7);
         // dH = [d sdf_emb (dgrad of layer 3), d rgb_emb (colour head)]
         if (q < 2) {
             tb_load32(c, TB_D + 32 * q, v);
@@ -406,7 +435,8 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
         { float t[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) t[k] = v[k];
-          aB2 += rs32(t, lane); }
+          atomicAdd(&c.sacc[SA_B2 + 32 * q + lane], rs32(t, lane)); }
+        TB_MARK(8);
         // ---- layer 2: wgrad (X = H1 from operand 1), then dgrad ----
         tb_wgrad_layer(c, p, q, v,
             [&](uint32_t (&xh)[16], uint32_t (&xl)[16]) {
@@ -415,6 +445,7 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
                 return true;
             },
             D_H, gpart + OFF_W2, D_H, [](int k) { return k; });
+        TB_MARK(9);
         tb_store_op32(c, TB_OP2_HI, TB_OP2_LO, q, v);                        // dH
         tb_round(c, [&]() { tb_issue_dgrad(c, c.w2, c.w2 + 2 * IMG_BLOCK, D_H); });
         tb_load32(c, TB_D + 32 * q, v);
@@ -423,35 +454,48 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
         { float t[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) t[k] = v[k];
-          aB1 += rs32(t, lane); }
-        // ---- layer 1: wgrad (X = e, 64 slots: this thread owns slots [16q, 16q+16)) ----
+          atomicAdd(&c.sacc[SA_B1 + 32 * q + lane], rs32(t, lane)); }
+        TB_MARK(10);
+        // ---- layer 1: wgrad (X = e, 64 slots: this thread owns slots [16q, 16q+16), recomputed here) ----
         {
             uint8_t *z_hi = c.r1, *z_lo = c.r1 + 2 * HALF_BLK, *x_hi = c.r2, *x_lo = c.r2 + 2 * HALF_BLK;
-            uint32_t zh[16], zl[16], xh[8], xl[8];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) umma::split2(v[2 * k], v[2 * k + 1], zh[k], zl[k]);
-#pragma unroll
-            for (int t = 0; t < 8; ++t) umma::split2(e[2 * t], e[2 * t + 1], xh[t], xl[t]);
             for (int half = 0; half < 2; ++half) {
                 if ((p >> 6) == half) {
                     const int row = p & 63;
-                    umma::store_row32(z_hi, row, q, zh, HALF_BLK);
-                    umma::store_row32(z_lo, row, q, zl, HALF_BLK);
-                    umma::store_row16(x_hi, row, q, xh);
-                    umma::store_row16(x_lo, row, q, xl);
+                    {
+                        uint32_t zh[16], zl[16];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) umma::split2(v[2 * k], v[2 * k + 1], zh[k], zl[k]);
+                        umma::store_row32(z_hi, row, q, zh, HALF_BLK);
+                        umma::store_row32(z_lo, row, q, zl, HALF_BLK);
+                    }
+                    {
+                        float e[16];
+                        tb_e_slots(x, q, e);
+                        uint32_t xh[8], xl[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) umma::split2(e[2 * t], e[2 * t + 1], xh[t], xl[t]);
+                        umma::store_row16(x_hi, row, q, xh);
+                        umma::store_row16(x_lo, row, q, xl);
+                    }
                 }
                 tb_round(c, [&]() { tb_issue_wgrad(c, 64, half == 0); });
             }
             if (q < 2) {
-                float d[32];
-                tb_load32(c, TB_D + 32 * q, d);
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const int ei = tc_e_slot_to_index(32 * q + k);
-                    if (ei >= 0) gpart[OFF_W1 + p * D_E + ei] += d[k];
+                for (int c0 = 0; c0 < 32; c0 += 8) {
+                    uint32_t r[8];
+                    umma::tmem_ld8(c.lane_base + (uint32_t)(TB_D + 32 * q + c0), r);
+                    umma::wait_ld();
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int ei = tc_e_slot_to_index(32 * q + c0 + k);
+                        if (ei >= 0) atomicAdd(&gpart[OFF_W1 + ei * D_H + p], __uint_as_float(r[k]));
+                    }
                 }
             }
         }
+        TB_MARK(11);
         if (WANT_DX) {
             // ---- dgrad of layer 1: dE (64 slots) = dZ1 W1, plus the colour head's direct use of e ----
             tb_store_op32(c, TB_OP2_HI, TB_OP2_LO, q, v);                    // dZ1
@@ -486,33 +530,23 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
                 d_pts[i * 3 + 0] = dp[0]; d_pts[i * 3 + 1] = dp[1]; d_pts[i * 3 + 2] = dp[2];
             }
         }
+        TB_MARK(12);
         umma::fence_before_sync();
         __syncthreads();           // accumulator / operand reads of this tile are done before the next tile reuses them
     }
 
     // ---- flush the narrow-head and bias accumulators into this CTA's partial ----
     __syncthreads();
-#pragma unroll
-    for (int ch = 0; ch < N_CLASS; ++ch) atomicAdd(&gpart[OFF_WS2 + ch * D_H + 32 * q + lane], aW4[ch]);
-    if (q >= 2) {
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) atomicAdd(&gpart[OFF_WR + ch * D_RGB_IN + 32 * (q - 2) + lane], aWrEmb[ch]);
-    }
-    if (lane < 16) {
-        const int ei = tc_e_slot_to_index(16 * q + lane);
-        if (ei >= 0) {
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) atomicAdd(&gpart[OFF_WR + ch * D_RGB_IN + 64 + ei], aWrE[ch]);
-        }
-    }
-    atomicAdd(&gpart[OFF_B1 + 32 * q + lane], aB1);
-    atomicAdd(&gpart[OFF_B2 + 32 * q + lane], aB2);
-    atomicAdd(&gpart[OFF_BS1 + 32 * q + lane], aBs1);
-    if (q == 0 && lane == 0) {
-#pragma unroll
-        for (int ch = 0; ch < N_CLASS; ++ch) atomicAdd(&gpart[OFF_BS2 + ch], aB4[ch]);
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) atomicAdd(&gpart[OFF_BR + ch], aBr[ch]);
+    for (int j = tid; j < SA_COUNT; j += TC_NT) {
+        int dst;
+        if (j < SA_WR) dst = OFF_WS2 + j;
+        else if (j < SA_B1) dst = OFF_WR + (j - SA_WR);
+        else if (j < SA_B2) dst = OFF_B1 + (j - SA_B1);
+        else if (j < SA_BS1) dst = OFF_B2 + (j - SA_B2);
+        else if (j < SA_B4) dst = OFF_BS1 + (j - SA_BS1);
+        else if (j < SA_BR) dst = OFF_BS2 + (j - SA_B4);
+        else dst = OFF_BR + (j - SA_BR);
+        gpart[dst] += c.sacc[j];
     }
     if (!c.ok && err) atomicExch(err, 1);
     umma::fence_before_sync();

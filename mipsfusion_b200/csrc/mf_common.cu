@@ -66,3 +66,29 @@ MF_API int mf_tc_check_error(void) {
     if (v) MF_CUDA(cudaMemset(p, 0, sizeof(int)));
     return v;
 }
+
+// ---- in-kernel phase profiling (diagnostics) -----------------------------------------------------
+static long long* g_prof[64] = {nullptr};
+static int g_prof_on = 0;
+long long* mf_tc_profile_buffer() {
+    if (!g_prof_on) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!g_prof[dev]) {
+        if (cudaMalloc(&g_prof[dev], 64 * sizeof(long long)) != cudaSuccess) return nullptr;
+        cudaMemset(g_prof[dev], 0, 64 * sizeof(long long));
+    }
+    return g_prof[dev];
+}
+// Enable (on != 0) / disable the clock stamps the tensor-core backward kernel records for its second tile on
+// CTA 0; out_host (64 int64, may be NULL) receives the last recorded stamps.  Synchronises the device.
+MF_API int mf_debug_profile(int on, long long* out_host) {
+    g_prof_on = on ? 1 : 0;
+    if (out_host) {
+        int dev = 0;
+        MF_CUDA(cudaGetDevice(&dev));
+        if (g_prof[dev]) MF_CUDA(cudaMemcpy(out_host, g_prof[dev], 64 * sizeof(long long), cudaMemcpyDeviceToHost));
+        else memset(out_host, 0, 64 * sizeof(long long));
+    }
+    return MF_OK;
+}

@@ -94,7 +94,8 @@ struct FieldDev {
 
 int mf_field_to_dev(const mf_field* f, FieldDev* d);   // validates (16 levels, 2 features)
 int mf_decoder_impl();                                 // 0: tcgen05 tensor cores (default), 1: fp32 CUDA cores
-int* mf_tc_error_flag();                               // device int, set by a kernel whose MMA wait timed out
+int* mf_tc_error_flag();
+long long* mf_tc_profile_buffer();                     // device buffer of 64 clock stamps, or nullptr when profiling is off                               // device int, set by a kernel whose MMA wait timed out
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
