@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from . import dist as D
 
 
 def get_grid_uniform(xyz_min, xyz_max, padding=0.05, voxel_size=0.05):
@@ -71,17 +72,13 @@ class JointSubmapQuery:
         dev = self.device
         ps, keep_ps, total = self._point_set(points, axes)
         subs, keep_sub = self._submaps()
-        ws, rk = 1, 0
-        if group is not None:
-            import torch.distributed as dist
-            ws, rk = dist.get_world_size(group), dist.get_rank(group)
+        ws, rk = D.world(group)
         g_begin, g_count = 0, total
         m_sel = list(range(self.M))
         if ws > 1 and shard == "points":
-            per = (total + ws - 1) // ws
-            g_begin = min(rk * per, total); g_count = min(per, total - g_begin)
+            g_begin, g_count, _ = D.shard_range(total, ws, rk)
         elif ws > 1:
-            m_sel = [m for m in range(self.M) if m % ws == rk]
+            m_sel = D.round_robin(self.M, ws, rk)
         K = 4 if color else 2
         st = L.stream()
         max_dist = torch.zeros(self.M, device=dev, dtype=torch.float32)
@@ -95,22 +92,16 @@ class JointSubmapQuery:
         with torch.cuda.device(dev):
             L.call("mf_joint_query_maxdist", C.byref(ps), subs, self.M, g_begin, g_count, L.ptr(max_dist), st)
             if ws > 1 and shard == "points":
-                import torch.distributed as dist
-                dist.all_reduce(max_dist, op=dist.ReduceOp.MAX, group=group)
+                D.allreduce_max_(max_dist, group)
             # contiguous runs of selected submaps
             for m in m_sel:
                 L.call("mf_joint_query_accumulate", C.byref(ps), subs, self.M, m, 1, L.ptr(max_dist), L.ptr(vis_t), int(color),
                        g_begin, g_count, L.ptr(acc), L.ptr(mask_any), L.ptr(contain), L.ptr(scratch), st)
             if ws > 1 and shard == "submaps":
-                import torch.distributed as dist
-                dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
-                mi = mask_any.to(torch.int32)
-                dist.all_reduce(mi, op=dist.ReduceOp.MAX, group=group)
-                mask_any = mi.to(torch.uint8)
+                D.allreduce_sum_(acc, group)
+                mask_any = D.allreduce_max_(mask_any.to(torch.int32), group).to(torch.uint8)
                 if contain is not None:
-                    ci = contain.to(torch.int32)
-                    dist.all_reduce(ci, op=dist.ReduceOp.MAX, group=group)
-                    contain = ci.to(torch.uint8)
+                    contain = D.allreduce_max_(contain.to(torch.int32), group).to(torch.uint8)
             out = torch.empty(max(g_count, 1), K - 1, device=dev, dtype=torch.float32)
             L.call("mf_joint_query_finalize", L.ptr(acc), L.ptr(mask_any), int(color), g_count, L.ptr(out), st)
         res = {"mask": mask_any[:g_count].bool(), "range": (g_begin, g_count), "max_dist": max_dist}

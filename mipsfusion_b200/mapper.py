@@ -12,6 +12,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
+from . import dist as D
 from .decoder import _Workspace
 
 
@@ -25,10 +26,7 @@ class FusedMapper:
         self.lr_decoder = cfg["mapping"]["lr_decoder"] if lr_decoder is None else lr_decoder
         self.lr_embed = cfg["mapping"]["lr_embed"] if lr_embed is None else lr_embed
         self.group = group
-        self.world = 1
-        if group is not None:
-            import torch.distributed as dist
-            self.world = dist.get_world_size(group)
+        self.world = D.world(group)[0]
         t = cfg["training"]
         # d(total loss)/d(rgb, depth, sdf, fs loss): the weights of get_loss_from_ret (mipsfusion.py:142-152)
         self.loss_w = torch.tensor([t["rgb_weight"], t["depth_weight"], t["sdf_weight"], t["fs_weight"]], dtype=torch.float32,
@@ -86,9 +84,7 @@ class FusedMapper:
         e0 = ev()
         L.call("mf_sample_z", L.ptr(target_d), L.ptr(u), L.ptr(lins[0]), L.ptr(lins[1]), L.ptr(lins[2]), C.byref(cfg),
                L.ptr(b["z"]), L.ptr(b["counts"]), R, st)
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(b["counts"], group=self.group)           # batch-global mask counts
+        D.allreduce_sum_(b["counts"], self.group)                    # batch-global mask counts (utils.py:43-47)
         e1 = ev()
         L.call("mf_field_query_rays", L.ptr(rays_o), L.ptr(rays_d), L.ptr(b["z"]), C.byref(field), L.ptr(b["raw"]), R, S, st)
         e2 = ev()
@@ -102,11 +98,7 @@ class FusedMapper:
         e4 = ev()
         self.launches += 7
         if update:
-            if self.world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(self.g_grid, group=self.group)
-                dist.all_reduce(self.g_mlp, group=self.group)
-                self.g_grid.mul_(1.0 / self.world); self.g_mlp.mul_(1.0 / self.world)
+            D.average_gradients_([self.g_grid, self.g_mlp], self.group)
             self.apply_gradients()
         e5 = ev()
         if tm is not None:

@@ -10,6 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from . import dist as D
 from .sampling_helper import sample_pixels_uniformly
 
 
@@ -52,13 +53,9 @@ class RandomOptimizer:
     # ---- sharding ---------------------------------------------------------------------------------
     def _shard(self):
         Cn = self.pre_sampled_particle.shape[0]
-        if self.group is None:
-            return 0, Cn, 1, 0
-        import torch.distributed as dist
-        ws, rk = dist.get_world_size(self.group), dist.get_rank(self.group)
-        per = (Cn + ws - 1) // ws
-        b = min(rk * per, Cn)
-        return b, min(per, Cn - b), ws, rk
+        ws, rk = D.world(self.group)
+        b, n, _ = D.shard_range(Cn, ws, rk)
+        return b, n, ws, rk
 
     def score(self, model, rot_cur, trans_cur, search_size, target_d, rays_d_cam):
         """Fitness of every candidate (RandomOptimizer.py:113-131).  All arguments are device tensors:
@@ -78,11 +75,8 @@ class RandomOptimizer:
                    int(b), int(n), int(P), L.ptr(fit), L.ptr(msdf), L.ptr(pst7), L.ptr(scratch), L.stream())
         if ws == 1:
             return fit[:Cn], msdf[:Cn], pst7[:Cn]
-        import torch.distributed as dist
         packed[:, 0], packed[:, 1], packed[:, 2:] = fit, msdf, pst7
-        gathered = torch.empty(ws * per, 9, device=dev, dtype=torch.float32)
-        dist.all_gather_into_tensor(gathered, packed, group=self.group)
-        gathered = gathered[:Cn]
+        gathered = D.allgather_rows(packed, Cn, self.group)          # one small all-gather: 9 floats per candidate
         return gathered[:, 0].contiguous(), gathered[:, 1].contiguous(), gathered[:, 2:].contiguous()
 
     def update(self, fitness, mean_sdf, pst7, rot_cur, trans_cur, search_size):
