@@ -130,7 +130,7 @@ def run_reference(args):
     val = n_rays * args.steps / dt
     cores = torch.get_num_threads()
     sample = f"{args.steps} steps x {n_rays} rays x {S} samples (1/{R_RAYS // n_rays} of the 4096-ray batch), full T=2^19 grid + dense Adam"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": "map_step_rays_per_s", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -211,7 +211,7 @@ def run_gpu(args):
 
     if args.quick:                    # profiling runs (ncu): only the timed steps above
         if rank == 0:
-            print(json.dumps({"metric": "map_step_rays_per_s", "value": value, "ms_per_step": dev_ms / args.steps, "quick": True}))
+            emit({"metric": "map_step_rays_per_s", "value": value, "ms_per_step": dev_ms / args.steps, "quick": True})
         return
     # ---- per-kernel timing of the dominant kernel (separate pass, events around each launch) ----
     mapper.timing = {}
@@ -294,7 +294,7 @@ def run_gpu(args):
            "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": 4,
                    "api": "JointEncoding.forward + loss.backward() + FusedAdam.step()"},
            "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": t_wall, "also": also}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -338,7 +338,18 @@ def tracking_bench(model, cfg, dev, iters=5):
             "tracking_shape": f"{Cn} candidates x {nr * nc} pixels, SDF-only field query + per-candidate reduction + swarm update"}
 
 
+def emit(obj):
+    """Write the single JSON line to the real stdout (fd 1 is pointed at stderr while the bench runs so that
+    library banners such as NCCL's version line cannot pollute it)."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

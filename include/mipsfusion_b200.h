@@ -146,12 +146,16 @@ int mf_sample_z(const float* target_d, const float* u, const float* lin_uniform,
                 int64_t R, void* stream);
 
 /* ---- a4+a12 fused: points on rays pts = o + d z, field query -> raw (R,S,10) ---- */
+/* feat (optional, NULL to skip): cache of the encoded features, mf_feat_cache_size(R*S) bytes, written by the
+ * forward and consumed by mf_field_query_rays_bwd so that the backward does not repeat the table gathers
+ * (tensor-core decoder only; ignored by the fp32 decoder). */
+int64_t mf_feat_cache_size(int64_t n_points);
 int mf_field_query_rays(const float* rays_o, const float* rays_d, const float* z, const mf_field* field_host,
-                        float* raw, int64_t R, int S, void* stream);
+                        float* raw, void* feat, int64_t R, int S, void* stream);
 /* d_raw (R,S,10) -> grad_grid, grad_mlp (accumulate), d_rays_o / d_rays_d (R,3; optional, overwritten). */
 int mf_field_query_rays_bwd(const float* rays_o, const float* rays_d, const float* z, const mf_field* field_host,
-                            const float* d_raw, float* grad_grid, float* grad_mlp, float* d_rays_o, float* d_rays_d,
-                            float* workspace, int64_t R, int S, void* stream);
+                            const float* d_raw, const void* feat, float* grad_grid, float* grad_mlp, float* d_rays_o,
+                            float* d_rays_d, float* workspace, int64_t R, int S, void* stream);
 
 /* ---- a6-a8: SDF->weights rendering + losses (scene_rep.py:58-103,190-238; helper_functions/utils.py:21-111) ----
  * out_rgb (R,3), out_depth (R), out_aux (R,3) = depth_var, disp_map, acc_map (optional); out_weights (R,S) normalised

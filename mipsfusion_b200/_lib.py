@@ -72,8 +72,9 @@ PROTOTYPES = {
     "mf_field_query": (_I, [_P, C.POINTER(Field), _I, _P, _L, _P]),
     "mf_field_query_bwd": (_I, [_P, C.POINTER(Field), _I, _P, _P, _P, _P, _P, _L, _P]),
     "mf_sample_z": (_I, [_P, _P, _P, _P, _P, C.POINTER(RenderCfg), _P, _P, _L, _P]),
-    "mf_field_query_rays": (_I, [_P, _P, _P, C.POINTER(Field), _P, _L, _I, _P]),
-    "mf_field_query_rays_bwd": (_I, [_P, _P, _P, C.POINTER(Field), _P, _P, _P, _P, _P, _P, _L, _I, _P]),
+    "mf_feat_cache_size": (_L, [_L]),
+    "mf_field_query_rays": (_I, [_P, _P, _P, C.POINTER(Field), _P, _P, _L, _I, _P]),
+    "mf_field_query_rays_bwd": (_I, [_P, _P, _P, C.POINTER(Field), _P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
     "mf_render_loss_fwd": (_I, [_P, _P, _P, _P, _P, C.POINTER(RenderCfg), _P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
     "mf_render_loss_bwd": (_I, [_P, _P, _P, _P, _P, _P, C.POINTER(RenderCfg), _P, _P, _P, _P, _L, _I, _P]),
     "mf_adam_step": (_I, [_P, _P, _P, _P, _L, _D, _D, _D, _D, _D, _I, _I, _P]),

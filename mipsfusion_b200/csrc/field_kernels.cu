@@ -265,7 +265,7 @@ int mf_field_to_dev(const mf_field* f, FieldDev* d) {
         mf_set_error("fused field kernels are built for 16 levels x 2 features (got %d x %d)", f->meta.n_levels, f->meta.n_features);
         return MF_ERR_UNSUPPORTED;
     }
-    d->grid = f->grid; d->prep = f->mlp_prep;
+    d->grid = f->grid; d->prep = f->mlp_prep; d->feat = nullptr;
     d->tc_img = reinterpret_cast<const uint8_t*>(f->mlp_prep + PREP_TC);
     for (int k = 0; k < 3; ++k) { d->na[k] = f->norm_a[k]; d->nb[k] = f->norm_b[k]; }
     d->nf = f->norm_factor;
@@ -467,24 +467,30 @@ MF_API int mf_field_query_bwd(const float* pts, const mf_field* field, int norma
     return launch_field_bwd(d, src, d_out, grad_grid, grad_mlp, d_pts, workspace, N, (cudaStream_t)stream);
 }
 
+MF_API int64_t mf_feat_cache_size(int64_t n_points) {
+    return ((n_points + TC_TP - 1) / TC_TP) * (int64_t)FEAT_TILE_WORDS * 4;
+}
+
 MF_API int mf_field_query_rays(const float* rays_o, const float* rays_d, const float* z, const mf_field* field, float* raw,
-                               int64_t R, int S, void* stream) {
+                               void* feat, int64_t R, int S, void* stream) {
     MF_CHECK_ARG(R >= 0 && S > 0);
     if (R == 0) return MF_OK;
     MF_CHECK_ARG(rays_o && rays_d && z && raw);
     FieldDev d; int rc = mf_field_to_dev(field, &d); if (rc) return rc;
+    d.feat = (uint32_t*)feat;
     SrcRays src{rays_o, rays_d, z, S};
     return launch_field_fwd_auto<SrcRays, EpiRaw, false>(d, src, EpiRaw{raw}, R * S, (cudaStream_t)stream);
 }
 
 MF_API int mf_field_query_rays_bwd(const float* rays_o, const float* rays_d, const float* z, const mf_field* field,
-                                   const float* d_raw, float* grad_grid, float* grad_mlp, float* d_rays_o, float* d_rays_d,
-                                   float* workspace, int64_t R, int S, void* stream) {
+                                   const float* d_raw, const void* feat, float* grad_grid, float* grad_mlp, float* d_rays_o,
+                                   float* d_rays_d, float* workspace, int64_t R, int S, void* stream) {
     MF_CHECK_ARG(R >= 0 && S > 0);
     if (R == 0) return MF_OK;
     MF_CHECK_ARG(rays_o && rays_d && z && d_raw && grad_grid && grad_mlp && workspace);
     MF_CHECK_ARG((d_rays_o == nullptr) == (d_rays_d == nullptr));
     FieldDev d; int rc = mf_field_to_dev(field, &d); if (rc) return rc;
+    d.feat = (uint32_t*)feat;
     SrcRays src{rays_o, rays_d, z, S};
     cudaStream_t st = (cudaStream_t)stream;
     // the per-point dL/dp buffer lives behind the per-CTA partials in the workspace

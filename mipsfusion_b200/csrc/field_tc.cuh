@@ -16,6 +16,11 @@
 constexpr int TC_TP = 128;               // points per tile = UMMA M
 constexpr int TC_NT = 512;               // threads per CTA: 4 threads per point
 constexpr int TC_LD = TC_TP + 4;         // row length of the small fp32 staging arrays
+// Encoded-feature cache (optional): the packed bf16 hi/lo operand words a thread writes to tensor memory at
+// encode time, kept in HBM so the backward need not redo the gathers.  Per tile [q 4][word 24][p 128] uint32:
+// words 0..7 e_hi, 8..15 e_lo, 16..19 grid_hi, 20..23 grid_lo (384 B per point).
+constexpr int FEAT_WORDS = 24;
+constexpr int FEAT_TILE_WORDS = 4 * FEAT_WORDS * TC_TP;
 
 // ---- weight image (built by mf_mlp_prepare, copied once per CTA into shared memory) -----------
 // bf16 K-major blocks of 128 rows (output n) x 64 k, 128-byte swizzle, 16 KB each.
@@ -180,6 +185,11 @@ __device__ __forceinline__ void tc_encode_tile(const TcCtx& c, const FieldDev& f
         for (int t = 0; t < 8; ++t) umma::split2(e[2 * t], e[2 * t + 1], hi[t], lo[t]);
         umma::tmem_st8(c.lane_base + TM_A_HI + 8 * q, hi);
         umma::tmem_st8(c.lane_base + TM_A_LO + 8 * q, lo);
+        if (f.feat) {
+            uint32_t* fo = f.feat + (size_t)tile * FEAT_TILE_WORDS + (size_t)q * FEAT_WORDS * TC_TP + p;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { fo[t * TC_TP] = hi[t]; fo[(8 + t) * TC_TP] = lo[t]; }
+        }
     }
     if (!SDF_ONLY) {
         const float* wre = c.fw + F_WR_E + 16 * q;
@@ -205,6 +215,11 @@ __device__ __forceinline__ void tc_encode_tile(const TcCtx& c, const FieldDev& f
         for (int t = 0; t < 4; ++t) umma::split2(g[2 * t], g[2 * t + 1], hi[t], lo[t]);
         umma::tmem_st4(c.lane_base + TM_G_HI + 4 * q, hi);
         umma::tmem_st4(c.lane_base + TM_G_LO + 4 * q, lo);
+        if (f.feat) {
+            uint32_t* fo = f.feat + (size_t)tile * FEAT_TILE_WORDS + (size_t)q * FEAT_WORDS * TC_TP + p;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { fo[(16 + t) * TC_TP] = hi[t]; fo[(20 + t) * TC_TP] = lo[t]; }
+        }
     }
 }
 

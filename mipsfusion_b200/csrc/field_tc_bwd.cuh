@@ -256,15 +256,26 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
         float g[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) g[k] = valid ? d_raw[i * MF_RAW_DIM + k] : 0.f;
-        // ---- encode ----
+        // ---- encode (or reload the operand words the forward kernel cached) ----
         float x[3] = {0.f, 0.f, 0.f};
         if (valid) src.point(i, f, x);
+        const uint32_t* fin = f.feat ? f.feat + (size_t)tile * FEAT_TILE_WORDS + (size_t)q * FEAT_WORDS * TC_TP + p : nullptr;
         {
             float e[16];
-            tb_e_slots(x, q, e);
             uint32_t hi[8], lo[8];
+            if (fin) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) umma::split2(e[2 * t], e[2 * t + 1], hi[t], lo[t]);
+                for (int t = 0; t < 8; ++t) { hi[t] = __ldg(fin + t * TC_TP); lo[t] = __ldg(fin + (8 + t) * TC_TP); }
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    e[2 * t] = __uint_as_float(hi[t] << 16) + __uint_as_float(lo[t] << 16);
+                    e[2 * t + 1] = __uint_as_float(hi[t] & 0xffff0000u) + __uint_as_float(lo[t] & 0xffff0000u);
+                }
+            } else {
+                tb_e_slots(x, q, e);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) umma::split2(e[2 * t], e[2 * t + 1], hi[t], lo[t]);
+            }
             umma::tmem_st8(c.lane_base + TB_OP1_HI + 8 * q, hi);
             umma::tmem_st8(c.lane_base + TB_OP1_LO + 8 * q, lo);
             // colour head, e part: dWr[c][64 + e_index(slot)] += dRGB[c] e[slot]
@@ -279,16 +290,21 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
             }
         }
         {
-            float gf[8];
-#pragma unroll
-            for (int ll = 0; ll < 4; ++ll) {
-                float2 v = make_float2(0.f, 0.f);
-                if (valid) v = grid_level_fwd(x, grid2, level_info(f, q * 4 + ll), nullptr);
-                gf[2 * ll] = v.x; gf[2 * ll + 1] = v.y;
-            }
             uint32_t hi[4], lo[4];
+            if (fin) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) umma::split2(gf[2 * t], gf[2 * t + 1], hi[t], lo[t]);
+                for (int t = 0; t < 4; ++t) { hi[t] = __ldg(fin + (16 + t) * TC_TP); lo[t] = __ldg(fin + (20 + t) * TC_TP); }
+            } else {
+                float gf[8];
+#pragma unroll
+                for (int ll = 0; ll < 4; ++ll) {
+                    float2 vv = make_float2(0.f, 0.f);
+                    if (valid) vv = grid_level_fwd(x, grid2, level_info(f, q * 4 + ll), nullptr);
+                    gf[2 * ll] = vv.x; gf[2 * ll + 1] = vv.y;
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) umma::split2(gf[2 * t], gf[2 * t + 1], hi[t], lo[t]);
+            }
             umma::tmem_st4(c.lane_base + TB_G_HI + 4 * q, hi);
             umma::tmem_st4(c.lane_base + TB_G_LO + 4 * q, lo);
         }
@@ -470,11 +486,16 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
                         umma::store_row32(z_lo, row, q, zl, HALF_BLK);
                     }
                     {
-                        float e[16];
-                        tb_e_slots(x, q, e);
                         uint32_t xh[8], xl[8];
+                        if (fin) {
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) umma::split2(e[2 * t], e[2 * t + 1], xh[t], xl[t]);
+                            for (int t = 0; t < 8; ++t) { xh[t] = __ldg(fin + t * TC_TP); xl[t] = __ldg(fin + (8 + t) * TC_TP); }
+                        } else {
+                            float e[16];
+                            tb_e_slots(x, q, e);
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) umma::split2(e[2 * t], e[2 * t + 1], xh[t], xl[t]);
+                        }
                         umma::store_row16(x_hi, row, q, xh);
                         umma::store_row16(x_lo, row, q, xl);
                     }

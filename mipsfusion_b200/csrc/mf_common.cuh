@@ -85,6 +85,7 @@ struct FieldDev {
     const float* grid;
     const float* prep;
     const uint8_t* tc_img;        // prep + PREP_TC: bf16 hi/lo weight image of the tcgen05 decoder
+    uint32_t* feat;               // optional encoded-feature cache written by the tc forward, read by the tc backward
     double na[3], nb[3], nf;
     int impl;                     // resolved decoder implementation: 0 tcgen05, 1 fp32 CUDA cores
     int n_levels;

@@ -52,7 +52,8 @@ class FusedMapper:
             b = dict(z=torch.empty(R, S, **f32), counts=torch.empty(2, device=d, dtype=torch.int64),
                      raw=torch.empty(R, S, L.MF_RAW_DIM, **f32), d_raw=torch.empty(R, S, L.MF_RAW_DIM, **f32),
                      rgb=torch.empty(R, 3, **f32), depth=torch.empty(R, **f32), losses=torch.zeros(8, **f32),
-                     scratch=torch.empty(R * 8, **f32), u=torch.empty(R, S, **f32))
+                     scratch=torch.empty(R * 8, **f32), u=torch.empty(R, S, **f32),
+                     feat=torch.empty(int(L.lib().mf_feat_cache_size(R * S)), device=d, dtype=torch.uint8))
             self._bufs[key] = b
         return b
 
@@ -86,7 +87,8 @@ class FusedMapper:
                L.ptr(b["z"]), L.ptr(b["counts"]), R, st)
         D.allreduce_sum_(b["counts"], self.group)                    # batch-global mask counts (utils.py:43-47)
         e1 = ev()
-        L.call("mf_field_query_rays", L.ptr(rays_o), L.ptr(rays_d), L.ptr(b["z"]), C.byref(field), L.ptr(b["raw"]), R, S, st)
+        L.call("mf_field_query_rays", L.ptr(rays_o), L.ptr(rays_d), L.ptr(b["z"]), C.byref(field), L.ptr(b["raw"]), L.ptr(b["feat"]),
+               R, S, st)
         e2 = ev()
         L.call("mf_render_loss_fwd", L.ptr(b["raw"]), L.ptr(b["z"]), L.ptr(target_rgb), L.ptr(target_d), L.ptr(b["counts"]),
                C.byref(cfg), L.ptr(b["rgb"]), L.ptr(b["depth"]), None, None, None, L.ptr(b["losses"]), L.ptr(b["scratch"]), R, S, st)
@@ -94,7 +96,7 @@ class FusedMapper:
                L.ptr(b["losses"]), C.byref(cfg), L.ptr(self.loss_w), None, None, L.ptr(b["d_raw"]), R, S, st)
         e3 = ev()
         L.call("mf_field_query_rays_bwd", L.ptr(rays_o), L.ptr(rays_d), L.ptr(b["z"]), C.byref(field), L.ptr(b["d_raw"]),
-               L.ptr(self.g_grid), L.ptr(self.g_mlp), None, None, L.ptr(_Workspace.get(self.dev)), R, S, st)
+               L.ptr(b["feat"]), L.ptr(self.g_grid), L.ptr(self.g_mlp), None, None, L.ptr(_Workspace.get(self.dev)), R, S, st)
         e4 = ev()
         self.launches += 7
         if update:

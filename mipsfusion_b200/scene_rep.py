@@ -88,7 +88,12 @@ class _RenderFn(torch.autograd.Function):
         L.call("mf_sample_z", L.ptr(target_d), L.ptr(u), L.ptr(lins[0]), L.ptr(lins[1]), L.ptr(lins[2]), C.byref(cfg), L.ptr(z),
                L.ptr(counts), R, st)
         raw = torch.empty(R, S, L.MF_RAW_DIM, device=dev, dtype=torch.float32)
-        L.call("mf_field_query_rays", L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), C.byref(field), L.ptr(raw), R, S, st)
+        # encoded-feature cache for the backward (tensor-core route, only when a backward can follow)
+        feat = None
+        if ctx.impl == 0 and torch.is_grad_enabled() and any(ctx.needs_input_grad):
+            feat = torch.empty(int(L.lib().mf_feat_cache_size(R * S)), device=dev, dtype=torch.uint8)
+        ctx.feat = feat
+        L.call("mf_field_query_rays", L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), C.byref(field), L.ptr(raw), L.ptr(feat), R, S, st)
         rgb = torch.empty(R, 3, device=dev, dtype=torch.float32)
         depth = torch.empty(R, device=dev, dtype=torch.float32)
         aux = torch.empty(R, 3, device=dev, dtype=torch.float32)
@@ -125,8 +130,8 @@ class _RenderFn(torch.autograd.Function):
         d_o = torch.empty_like(rays_o) if want_rays else None
         d_d = torch.empty_like(rays_d) if want_rays else None
         ws = _Workspace.get(dev, 3 * R * S if want_rays else 0)
-        L.call("mf_field_query_rays_bwd", L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), C.byref(field), L.ptr(d_raw), L.ptr(g_grid),
-               L.ptr(g_mlp), L.ptr(d_o), L.ptr(d_d), L.ptr(ws), R, S, st)
+        L.call("mf_field_query_rays_bwd", L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), C.byref(field), L.ptr(d_raw), L.ptr(ctx.feat),
+               L.ptr(g_grid), L.ptr(g_mlp), L.ptr(d_o), L.ptr(d_d), L.ptr(ws), R, S, st)
         return (d_o, d_d, None, None, None, None, None, g_grid, *_split(g_mlp, ctx.shapes))
 
 
