@@ -178,6 +178,11 @@ int mf_render_loss_bwd(const float* raw, const float* z, const float* target_rgb
 int mf_adam_step(float* p, float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                  double eps, double weight_decay, int step, int zero_grad, void* stream);
 
+/* The same update for a parameter group of n_tensors tensors (host arrays of device pointers and sizes). */
+int mf_adam_step_multi(int n_tensors, float* const* p_host, float* const* g_host, float* const* m_host,
+                       float* const* v_host, const int64_t* n_host, double lr, double beta1, double beta2, double eps,
+                       double weight_decay, int step, int zero_grad, void* stream);
+
 /* ---- a11: pixel samplers (helper_functions/sampling_helper.py:7-68), int64 outputs ---- */
 int mf_sample_pixels_uniform(int img_h, int img_w, int num_h, int num_w, int64_t* rows, int64_t* cols, void* stream);
 /* top-`num` of keys*mask(depth>0 [and not on the lattice]) by (value desc, index asc); keys (H*W) >= 0.

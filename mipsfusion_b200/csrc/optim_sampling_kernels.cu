@@ -78,6 +78,17 @@ MF_API int mf_adam_step(float* p, float* g, float* m, float* v, int64_t n, doubl
     return MF_OK;
 }
 
+MF_API int mf_adam_step_multi(int n_tensors, float* const* p, float* const* g, float* const* m, float* const* v,
+                              const int64_t* n, double lr, double beta1, double beta2, double eps, double weight_decay,
+                              int step, int zero_grad, void* stream) {
+    MF_CHECK_ARG(n_tensors >= 0 && (n_tensors == 0 || (p && g && m && v && n)));
+    for (int t = 0; t < n_tensors; ++t) {
+        const int rc = mf_adam_step(p[t], g[t], m[t], v[t], n[t], lr, beta1, beta2, eps, weight_decay, step, zero_grad, stream);
+        if (rc) return rc;
+    }
+    return MF_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Uniform lattice (sampling_helper.py:38-48).
 // ---------------------------------------------------------------------------------------------

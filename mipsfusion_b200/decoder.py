@@ -79,8 +79,8 @@ class MLP_reg(nn.Module):
                                         nn.Linear(n_hidden_branch, n_class), nn.Softmax(dim=-1))
 
     def ordered_params(self):
-        sd = dict(self.named_parameters())
-        return [sd[k] for k in PARAM_ORDER]
+        lins = (self.pts_linear[0], self.pts_linear[2], self.rgb_linear[0], self.sdf_linear[0], self.sdf_linear[2])
+        return [t for lin in lins for t in (lin.weight, lin.bias)]
 
     def flat_weights(self):
         """The state_dict tensors concatenated in order (MF_MLP_PARAMS floats)."""

@@ -1,6 +1,8 @@
 """Fused dense Adam (mf_adam_step): same update as ``torch.optim.Adam`` configured at reference
 mipsfusion.py:580-584 / InactiveMap.py:53-57 (betas, per-group lr / eps / L2 weight_decay), one kernel
 per parameter tensor, with the reference's ``zero_grad()`` optionally folded into the same pass."""
+import ctypes as C
+
 import torch
 
 from . import _lib as L
@@ -14,26 +16,38 @@ class FusedAdam(torch.optim.Optimizer):
     def step(self, closure=None, zero_grad=False):
         """One Adam update.  zero_grad=True also clears every gradient in the same kernel pass
         (gradient tensors are kept, as with ``zero_grad(set_to_none=False)``)."""
+        st = None
         for group in self.param_groups:
             b1, b2 = group["betas"]
-            for p in group["params"]:
-                if p.grad is None or p.numel() == 0:
-                    continue
-                if not p.is_cuda:
-                    raise L.MipsFusionB200Error("FusedAdam needs CUDA parameters (no CPU fallback)")
-                st = self.state[p]
-                if not st:
-                    st["step"] = 0
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                st["step"] += 1
-                g = p.grad
-                if not (p.is_contiguous() and g.is_contiguous()):
-                    raise L.MipsFusionB200Error("FusedAdam needs contiguous parameters and gradients")
-                with torch.cuda.device(p.device):
-                    L.call("mf_adam_step", L.ptr(p), L.ptr(g), L.ptr(st["exp_avg"]), L.ptr(st["exp_avg_sq"]), p.numel(),
-                           float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                           int(st["step"]), 1 if zero_grad else 0, L.stream())
+            ps = [p for p in group["params"] if p.grad is not None and p.numel() > 0]
+            if not ps:
+                continue
+            dev = ps[0].device
+            if dev.type != "cuda":
+                raise L.MipsFusionB200Error("FusedAdam needs CUDA parameters (no CPU fallback)")
+            step = None
+            for p in ps:
+                state = self.state[p]
+                if not state:
+                    state["step"] = 0
+                    state["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                state["step"] += 1
+                if step is None:
+                    step = state["step"]
+                if state["step"] != step or p.device != dev or not (p.is_contiguous() and p.grad.is_contiguous()):
+                    raise L.MipsFusionB200Error("FusedAdam: a parameter group must be contiguous, on one device and in step")
+            n = len(ps)
+            arr = C.c_void_p * n
+            P = arr(*[p.data_ptr() for p in ps]); G = arr(*[p.grad.data_ptr() for p in ps])
+            M = arr(*[self.state[p]["exp_avg"].data_ptr() for p in ps]); V = arr(*[self.state[p]["exp_avg_sq"].data_ptr() for p in ps])
+            N = (C.c_int64 * n)(*[p.numel() for p in ps])
+            with torch.cuda.device(dev):
+                if st is None:
+                    st = L.stream()
+                L.call("mf_adam_step_multi", n, P, G, M, V, N, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                       float(group["weight_decay"]), int(step), 1 if zero_grad else 0, st)
+            for p in ps:
                 torch.autograd.graph.increment_version(p)      # the kernel wrote p behind autograd's back
         return None
 

@@ -90,7 +90,7 @@ class _RenderFn(torch.autograd.Function):
         raw = torch.empty(R, S, L.MF_RAW_DIM, device=dev, dtype=torch.float32)
         # encoded-feature cache for the backward (tensor-core route, only when a backward can follow)
         feat = None
-        if ctx.impl == 0 and torch.is_grad_enabled() and any(ctx.needs_input_grad):
+        if ctx.impl == 0 and any(ctx.needs_input_grad):       # (grad mode is off inside Function.forward; this is the signal)
             feat = torch.empty(int(L.lib().mf_feat_cache_size(R * S)), device=dev, dtype=torch.uint8)
         ctx.feat = feat
         L.call("mf_field_query_rays", L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), C.byref(field), L.ptr(raw), L.ptr(feat), R, S, st)
