@@ -318,10 +318,11 @@ __device__ __forceinline__ void mlp_forward_tile(const float* __restrict__ prep,
 }
 
 // Coalesced store of a tile's outputs OUT[c][m] (row length ld, tp points per tile) to raw (N,10).
-__device__ __forceinline__ void store_raw_tile(const float* OUT, int ld, int tp, float* __restrict__ raw, int64_t tile, int64_t N) {
+__device__ __forceinline__ void store_raw_tile(const float* OUT, int ld, int tp, float* __restrict__ raw, int64_t tile, int64_t N,
+                                               int tid, int nthreads) {
     const int64_t base = tile * tp;
     const int nv = (int)min((int64_t)tp, N - base);
-    for (int idx = threadIdx.x; idx < nv * MF_RAW_DIM; idx += blockDim.x) {
+    for (int idx = tid; idx < nv * MF_RAW_DIM; idx += nthreads) {
         const int m = idx / MF_RAW_DIM, c = idx % MF_RAW_DIM;
         raw[base * MF_RAW_DIM + idx] = OUT[c * ld + m];
     }

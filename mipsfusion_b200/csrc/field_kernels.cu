@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(NT, 2) mlp_fwd_kernel(const float* embed, cons
         __syncthreads();
         mlp_forward_tile<false>(prep, sm, sm + ROW_H1 * LDA);
         __syncthreads();
-        store_raw_tile(sm + ROW_OUT * LDA, LDA, TP, out, tile, N);
+        store_raw_tile(sm + ROW_OUT * LDA, LDA, TP, out, tile, N, threadIdx.x, NT);
         __syncthreads();
     }
 }
@@ -418,7 +418,7 @@ MF_API int mf_mlp_bwd(const float* embed, const float* embed_pos, const float* p
 template <class Src>
 static int launch_field_bwd(const FieldDev& d, const Src& src, const float* d_raw, float* grad_grid, float* grad_mlp,
                             float* d_pts, float* workspace, int64_t N, cudaStream_t st) {
-    if (d.impl == 0) {                                 // tcgen05 path: 128-point tiles, one CTA per SM
+    if (d.impl != 1) {                                 // tcgen05 path: 128-point tiles, one CTA per SM
         const int64_t tiles = (N + TC_TP - 1) / TC_TP;
         const int64_t cap = mf_sm_count_cached();
         const int grid = (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);

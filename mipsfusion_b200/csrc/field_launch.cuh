@@ -4,11 +4,11 @@
 #include "field_core.cuh"
 
 // Epilogues see the tile's outputs as OUT[c][m]: c = 0..9 (rgb_raw 3, sdf, entropy, prob 5), m = point in tile,
-// row length ld, tp points per tile.
+// row length ld, tp points per tile; (tid, nthreads) enumerate the cooperating threads.
 struct EpiRaw {                          // write the (N,10) decoder output
     float* raw;
-    __device__ __forceinline__ void store(const float* OUT, int ld, int tp, int64_t tile, int64_t N) const {
-        store_raw_tile(OUT, ld, tp, raw, tile, N);
+    __device__ __forceinline__ void store(const float* OUT, int ld, int tp, int64_t tile, int64_t N, int tid, int nthreads) const {
+        store_raw_tile(OUT, ld, tp, raw, tile, N, tid, nthreads);
     }
 };
 
@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(NT, 2) field_fwd_kernel(FieldDev f, Src src, E
         __syncthreads();
         mlp_forward_tile<SDF_ONLY>(f.prep, sm, sm + ROW_H1 * LDA);
         __syncthreads();
-        epi.store(sm + ROW_OUT * LDA, LDA, TP, tile, N);
+        epi.store(sm + ROW_OUT * LDA, LDA, TP, tile, N, threadIdx.x, NT);
         __syncthreads();
     }
 }

@@ -310,19 +310,25 @@ __device__ __forceinline__ bool tc_mlp_forward_tile(TcCtx& c) {
 template <class Src, class Epi, bool SDF_ONLY>
 __global__ void __launch_bounds__(TC_NT, 1) field_fwd_tc_kernel(FieldDev f, Src src, Epi epi, int64_t N,
                                                                 const unsigned int* __restrict__ n_dev,
-                                                                const uint8_t* __restrict__ img, int* __restrict__ err) {
+                                                                const uint8_t* __restrict__ img, int* __restrict__ err,
+                                                                long long* __restrict__ prof) {
     extern __shared__ uint8_t smem_raw[];
+#define TC_MARK(k) do { if (prof && threadIdx.x == 0 && blockIdx.x == 0 && tile == (int64_t)gridDim.x) prof[32 + (k)] = clock64(); } while (0)
     if (n_dev) N = (int64_t)*n_dev;
     TcCtx c;
     tc_setup(c, smem_raw, img);
     bool ok = true;
     const int64_t n_tiles = (N + TC_TP - 1) / TC_TP;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        TC_MARK(0);
         tc_encode_tile<Src, SDF_ONLY>(c, f, src, tile, N);
+        TC_MARK(1);
         ok &= tc_mlp_forward_tile<SDF_ONLY>(c);
+        TC_MARK(2);
         __syncthreads();
-        epi.store(c.out, TC_LD, TC_TP, tile, N);
+        epi.store(c.out, TC_LD, TC_TP, tile, N, threadIdx.x, TC_NT);
         __syncthreads();
+        TC_MARK(3);
     }
     if (!ok && err) atomicExch(err, 1);
     tc_teardown(c);

@@ -2,6 +2,7 @@
 #pragma once
 #include "field_launch.cuh"
 #include "field_tc.cuh"
+#include "field_tc2.cuh"
 
 template <class Src, class Epi, bool SDF_ONLY>
 static inline int launch_field_fwd_tc(const FieldDev& d, const Src& src, const Epi& epi, int64_t N, cudaStream_t st,
@@ -10,7 +11,20 @@ static inline int launch_field_fwd_tc(const FieldDev& d, const Src& src, const E
     const int64_t tiles = (N + TC_TP - 1) / TC_TP;
     const int64_t cap = mf_sm_count_cached();
     const int grid = (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
-    field_fwd_tc_kernel<Src, Epi, SDF_ONLY><<<grid, TC_NT, SMEM_TC, st>>>(d, src, epi, N, n_dev, d.tc_img, mf_tc_error_flag());
+    field_fwd_tc_kernel<Src, Epi, SDF_ONLY><<<grid, TC_NT, SMEM_TC, st>>>(d, src, epi, N, n_dev, d.tc_img, mf_tc_error_flag(), mf_tc_profile_buffer());
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}
+
+// dual-pipeline kernel: two 128-point tiles in flight per CTA
+template <class Src, class Epi, bool SDF_ONLY>
+static inline int launch_field_fwd_tc2(const FieldDev& d, const Src& src, const Epi& epi, int64_t N, cudaStream_t st,
+                                       const unsigned int* n_dev = nullptr) {
+    int rc = set_smem(field_fwd_tc2_kernel<Src, Epi, SDF_ONLY>, SMEM_TC2); if (rc) return rc;
+    const int64_t pairs = ((N + TC_TP - 1) / TC_TP + 1) / 2;
+    const int64_t cap = mf_sm_count_cached();
+    const int grid = (int)(pairs < cap ? (pairs > 0 ? pairs : 1) : cap);
+    field_fwd_tc2_kernel<Src, Epi, SDF_ONLY><<<grid, 2 * T2_GT, SMEM_TC2, st>>>(d, src, epi, N, n_dev, d.tc_img, mf_tc_error_flag());
     MF_LAUNCH_CHECK();
     return MF_OK;
 }
@@ -18,6 +32,7 @@ static inline int launch_field_fwd_tc(const FieldDev& d, const Src& src, const E
 template <class Src, class Epi, bool SDF_ONLY>
 static inline int launch_field_fwd_auto(const FieldDev& d, const Src& src, const Epi& epi, int64_t N, cudaStream_t st,
                                         const unsigned int* n_dev = nullptr) {
-    if (d.impl == 0) return launch_field_fwd_tc<Src, Epi, SDF_ONLY>(d, src, epi, N, st, n_dev);
+    if (d.impl == 0) return launch_field_fwd_tc2<Src, Epi, SDF_ONLY>(d, src, epi, N, st, n_dev);
+    if (d.impl == 2) return launch_field_fwd_tc<Src, Epi, SDF_ONLY>(d, src, epi, N, st, n_dev);   // single pipeline (A/B)
     return launch_field_fwd<Src, Epi, SDF_ONLY>(d, src, epi, N, st, n_dev);
 }

@@ -83,8 +83,8 @@ struct SrcJoint {                       // compacted list entry -> world point -
 struct EpiJoint {
     PointSetDev ps; SubmapDev sub; const int* list; int64_t origin; int64_t c_begin;
     const uint8_t* vis; int M, m; const float* max_dist; int color; float* acc; uint8_t* mask_any;
-    __device__ __forceinline__ void store(const float* OUT, int ld, int tp, int64_t tile, int64_t N) const {
-        const int t = threadIdx.x;
+    __device__ __forceinline__ void store(const float* OUT, int ld, int tp, int64_t tile, int64_t N, int tid, int nthreads) const {
+        const int t = tid;
         const int64_t i = tile * tp + t;
         if (t >= tp || i >= N) return;
         const int64_t li = c_begin + list[i];                             // index relative to g_begin

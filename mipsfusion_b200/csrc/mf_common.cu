@@ -39,7 +39,7 @@ static int g_decoder_impl = 0;
 int mf_decoder_impl() { return g_decoder_impl; }
 
 MF_API int mf_set_decoder_impl(int impl) {
-    MF_CHECK_ARG(impl == 0 || impl == 1);
+    MF_CHECK_ARG(impl == 0 || impl == 1 || impl == 2);   // 2: single-pipeline tcgen05 forward (A/B comparisons)
     g_decoder_impl = impl;
     return MF_OK;
 }

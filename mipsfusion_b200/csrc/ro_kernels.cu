@@ -65,8 +65,8 @@ struct SrcRO {                             // world point of (candidate, pixel):
 
 struct EpiAbsSdf {                         // valid * |sdf * trunc| per (candidate, pixel)
     float* out; const float* depth; int P; float trunc;
-    __device__ __forceinline__ void store(const float* OUT, int ld, int tp, int64_t tile, int64_t N) const {
-        const int m = threadIdx.x;
+    __device__ __forceinline__ void store(const float* OUT, int ld, int tp, int64_t tile, int64_t N, int tid, int nthreads) const {
+        const int m = tid;
         const int64_t i = tile * tp + m;
         if (m < tp && i < N) {
             const float valid = depth[i % P] > 0.f ? 1.f : 0.f;

@@ -21,3 +21,6 @@ names = ["copyW1+encode", "L1+epi1", "L2+epi2", "L3+epi3", "heads+dz3", "wgrad3"
 for i in range(12):
     print(f"{names[i]:18s} {t[i+1]-t[i]:8d} cycles")
 print("total", t[12]-t[0])
+
+f = list(buf)[32:36]
+print("fwd kernel: encode", f[1]-f[0], " mlp", f[2]-f[1], " store", f[3]-f[2], " total", f[3]-f[0])
