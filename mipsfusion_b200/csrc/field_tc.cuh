@@ -176,7 +176,7 @@ __device__ __forceinline__ void tc_encode_tile(const TcCtx& c, const FieldDev& f
 #pragma unroll
     for (int jj = 0; jj < 12; ++jj) {
         const int j = q * 12 + jj, d = j >> 4, k = (j & 15) >> 1, s = j & 1;
-        e[jj] = sinf(freq_arg(x[d], k, s));
+        e[jj] = sin_reduced(freq_arg(x[d], k, s));
     }
     e[12] = q == 0 ? x[0] : 0.f; e[13] = q == 0 ? x[1] : 0.f; e[14] = q == 0 ? x[2] : 0.f; e[15] = 0.f;
     {

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(2 * T2_GT, 1) field_fwd_tc2_kernel(FieldDev f,
 #pragma unroll
             for (int jj = 0; jj < 12; ++jj) {
                 const int j = qq * 12 + jj, d = j >> 4, k = (j & 15) >> 1, s = j & 1;
-                e[jj] = sinf(freq_arg(x[d], k, s));
+                e[jj] = sin_reduced(freq_arg(x[d], k, s));
             }
             e[12] = qq == 0 ? x[0] : 0.f; e[13] = qq == 0 ? x[1] : 0.f; e[14] = qq == 0 ? x[2] : 0.f; e[15] = 0.f;
             uint32_t hi[8], lo[8];
@@ -173,8 +173,15 @@ __global__ void __launch_bounds__(2 * T2_GT, 1) field_fwd_tc2_kernel(FieldDev f,
         for (int half = 0; half < 2; ++half) {
             const int f0 = 64 * h + 32 * half;
             t2_load32(c, T2_D + f0, v);
+            {
+                const float4* b4 = reinterpret_cast<const float4*>(c.fw + F_B1 + f0);
 #pragma unroll
-            for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k] + c.fw[F_B1 + f0 + k], 0.f);
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const float4 b = b4[k4];
+                    v[4 * k4] = fmaxf(v[4 * k4] + b.x, 0.f); v[4 * k4 + 1] = fmaxf(v[4 * k4 + 1] + b.y, 0.f);
+                    v[4 * k4 + 2] = fmaxf(v[4 * k4 + 2] + b.z, 0.f); v[4 * k4 + 3] = fmaxf(v[4 * k4 + 3] + b.w, 0.f);
+                }
+            }
             t2_store32(c, f0, v);
         }
         // ---- pts_linear.2 ----
@@ -185,16 +192,27 @@ __global__ void __launch_bounds__(2 * T2_GT, 1) field_fwd_tc2_kernel(FieldDev f,
             for (int half = 0; half < 2; ++half) {
                 const int f0 = 64 * h + 32 * half;
                 t2_load32(c, T2_D + f0, v);
+                {
+                    const float4* b4 = reinterpret_cast<const float4*>(c.fw + F_B2 + f0);
 #pragma unroll
-                for (int k = 0; k < 32; ++k) v[k] += c.fw[F_B2 + f0 + k];
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        const float4 b = b4[k4];
+                        v[4 * k4] += b.x; v[4 * k4 + 1] += b.y; v[4 * k4 + 2] += b.z; v[4 * k4 + 3] += b.w;
+                    }
+                }
                 if (h == 0) {
                     t2_store32(c, f0, v);                    // sdf_emb -> features [0,64) of the layer-3 operand
                 } else if (!SDF_ONLY) {
-                    const float* wr = c.fw + F_WR_EMB + 32 * half;
 #pragma unroll
-                    for (int k = 0; k < 32; ++k)
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const float4* w4 = reinterpret_cast<const float4*>(c.fw + F_WR_EMB + ch * 64 + 32 * half);
 #pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) r[ch] = fmaf(wr[ch * 64 + k], v[k], r[ch]);
+                        for (int k4 = 0; k4 < 8; ++k4) {
+                            const float4 w = w4[k4];
+                            r[ch] = fmaf(w.x, v[4 * k4], r[ch]); r[ch] = fmaf(w.y, v[4 * k4 + 1], r[ch]);
+                            r[ch] = fmaf(w.z, v[4 * k4 + 2], r[ch]); r[ch] = fmaf(w.w, v[4 * k4 + 3], r[ch]);
+                        }
+                    }
                 }
             }
             if (h == 1 && !SDF_ONLY) {
@@ -213,12 +231,24 @@ __global__ void __launch_bounds__(2 * T2_GT, 1) field_fwd_tc2_kernel(FieldDev f,
             for (int half = 0; half < 2; ++half) {
                 const int f0 = 64 * h + 32 * half;
                 t2_load32(c, T2_D + f0, v);
-                const float* ws2 = c.fw + F_WS2 + f0;
+                {
+                    const float4* b4 = reinterpret_cast<const float4*>(c.fw + F_BS1 + f0);
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const float hh = fmaxf(v[k] + c.fw[F_BS1 + f0 + k], 0.f);
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        const float4 b = b4[k4];
+                        v[4 * k4] = fmaxf(v[4 * k4] + b.x, 0.f); v[4 * k4 + 1] = fmaxf(v[4 * k4 + 1] + b.y, 0.f);
+                        v[4 * k4 + 2] = fmaxf(v[4 * k4 + 2] + b.z, 0.f); v[4 * k4 + 3] = fmaxf(v[4 * k4 + 3] + b.w, 0.f);
+                    }
+                }
 #pragma unroll
-                    for (int ch = 0; ch < N_CLASS; ++ch) s[ch] = fmaf(ws2[ch * 128 + k], hh, s[ch]);
+                for (int ch = 0; ch < N_CLASS; ++ch) {
+                    const float4* w4 = reinterpret_cast<const float4*>(c.fw + F_WS2 + ch * 128 + f0);
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        const float4 w = w4[k4];
+                        s[ch] = fmaf(w.x, v[4 * k4], s[ch]); s[ch] = fmaf(w.y, v[4 * k4 + 1], s[ch]);
+                        s[ch] = fmaf(w.z, v[4 * k4 + 2], s[ch]); s[ch] = fmaf(w.w, v[4 * k4 + 3], s[ch]);
+                    }
                 }
             }
 #pragma unroll

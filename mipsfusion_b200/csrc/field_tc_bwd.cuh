@@ -163,7 +163,7 @@ __device__ __forceinline__ void tb_e_slots(const float (&x)[3], int q, float (&e
 #pragma unroll
     for (int jj = 0; jj < 12; ++jj) {
         const int j = q * 12 + jj, d = j >> 4, k = (j & 15) >> 1, s = j & 1;
-        e[jj] = sinf(freq_arg(x[d], k, s));
+        e[jj] = sin_reduced(freq_arg(x[d], k, s));
     }
     e[12] = q == 0 ? x[0] : 0.f; e[13] = q == 0 ? x[1] : 0.f; e[14] = q == 0 ? x[2] : 0.f; e[15] = 0.f;
 }
@@ -314,18 +314,30 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
         // ---- forward layer 1 ----
         tb_round(c, [&]() { tb_issue_fwd(c, c.r1, c.r1 + IMG_BLOCK, 4, [](int ks, bool lo) { return (lo ? TB_OP1_LO : TB_OP1_HI) + 8 * ks; }); });
         tb_load32(c, TB_D + 32 * q, v);
+        {
+            const float4* b4 = reinterpret_cast<const float4*>(c.fw + F_B1 + 32 * q);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            v[k] = fmaxf(v[k] + c.fw[F_B1 + 32 * q + k], 0.f);
-            mask1 |= (v[k] > 0.f ? 1u : 0u) << k;
+            for (int k4 = 0; k4 < 8; ++k4) {
+                const float4 b = b4[k4];
+                v[4 * k4] = fmaxf(v[4 * k4] + b.x, 0.f); v[4 * k4 + 1] = fmaxf(v[4 * k4 + 1] + b.y, 0.f);
+                v[4 * k4 + 2] = fmaxf(v[4 * k4 + 2] + b.z, 0.f); v[4 * k4 + 3] = fmaxf(v[4 * k4 + 3] + b.w, 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < 32; ++k) mask1 |= (v[k] > 0.f ? 1u : 0u) << k;
         }
         tb_store_op32(c, TB_OP1_HI, TB_OP1_LO, q, v);                        // H1 stays in operand 1 until wgrad of layer 2
         TB_MARK(2);
         // ---- forward layer 2 ----
         tb_round(c, [&]() { tb_issue_fwd(c, c.w2, c.w2 + 2 * IMG_BLOCK, 8, [](int ks, bool lo) { return (lo ? TB_OP1_LO : TB_OP1_HI) + 8 * ks; }); });
         tb_load32(c, TB_D + 32 * q, v);
+        {
+            const float4* b4 = reinterpret_cast<const float4*>(c.fw + F_B2 + 32 * q);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] += c.fw[F_B2 + 32 * q + k];
+            for (int k4 = 0; k4 < 8; ++k4) {
+                const float4 b = b4[k4];
+                v[4 * k4] += b.x; v[4 * k4 + 1] += b.y; v[4 * k4 + 2] += b.z; v[4 * k4 + 3] += b.w;
+            }
+        }
         if (q < 2) {
             tb_store_op32(c, TB_OP2_HI, TB_OP2_LO, q, v);                    // sdf_emb
         } else {                                                             // colour head, rgb_emb part
@@ -347,13 +359,24 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
         tb_load32(c, TB_D + 32 * q, v);
         {
             float s[N_CLASS] = {0.f, 0.f, 0.f, 0.f, 0.f};
-            const float* ws2 = c.fw + F_WS2 + 32 * q;
+            const float4* b4 = reinterpret_cast<const float4*>(c.fw + F_BS1 + 32 * q);
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                v[k] = fmaxf(v[k] + c.fw[F_BS1 + 32 * q + k], 0.f);
-                mask3 |= (v[k] > 0.f ? 1u : 0u) << k;
+            for (int k4 = 0; k4 < 8; ++k4) {
+                const float4 b = b4[k4];
+                v[4 * k4] = fmaxf(v[4 * k4] + b.x, 0.f); v[4 * k4 + 1] = fmaxf(v[4 * k4 + 1] + b.y, 0.f);
+                v[4 * k4 + 2] = fmaxf(v[4 * k4 + 2] + b.z, 0.f); v[4 * k4 + 3] = fmaxf(v[4 * k4 + 3] + b.w, 0.f);
+            }
 #pragma unroll
-                for (int ch = 0; ch < N_CLASS; ++ch) s[ch] = fmaf(ws2[ch * 128 + k], v[k], s[ch]);
+            for (int k = 0; k < 32; ++k) mask3 |= (v[k] > 0.f ? 1u : 0u) << k;
+#pragma unroll
+            for (int ch = 0; ch < N_CLASS; ++ch) {
+                const float4* w4 = reinterpret_cast<const float4*>(c.fw + F_WS2 + ch * 128 + 32 * q);
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const float4 w = w4[k4];
+                    s[ch] = fmaf(w.x, v[4 * k4], s[ch]); s[ch] = fmaf(w.y, v[4 * k4 + 1], s[ch]);
+                    s[ch] = fmaf(w.z, v[4 * k4 + 2], s[ch]); s[ch] = fmaf(w.w, v[4 * k4 + 3], s[ch]);
+                }
             }
 #pragma unroll
             for (int ch = 0; ch < N_CLASS; ++ch) c.part[(q * 5 + ch) * TC_LD + p] = s[ch];
@@ -400,14 +423,21 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
         }
         // dZ3 = (Ws2^T dz4) * relu'(h3)
         {
-            const float* ws2 = c.fw + F_WS2 + 32 * q;
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                float s = 0.f;
+            for (int k = 0; k < 32; ++k) v[k] = 0.f;
 #pragma unroll
-                for (int ch = 0; ch < N_CLASS; ++ch) s = fmaf(ws2[ch * 128 + k], dz4[ch], s);
-                v[k] = ((mask3 >> k) & 1u) ? s : 0.f;
+            for (int ch = 0; ch < N_CLASS; ++ch) {
+                const float4* w4 = reinterpret_cast<const float4*>(c.fw + F_WS2 + ch * 128 + 32 * q);
+                const float dzc = dz4[ch];
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const float4 w = w4[k4];
+                    v[4 * k4] = fmaf(w.x, dzc, v[4 * k4]); v[4 * k4 + 1] = fmaf(w.y, dzc, v[4 * k4 + 1]);
+                    v[4 * k4 + 2] = fmaf(w.z, dzc, v[4 * k4 + 2]); v[4 * k4 + 3] = fmaf(w.w, dzc, v[4 * k4 + 3]);
+                }
             }
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = ((mask3 >> k) & 1u) ? v[k] : 0.f;
         }
         { float t[32];
 #pragma unroll
@@ -533,7 +563,7 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
                 const float de = __uint_as_float(r[s]) + fmaf(wre[128 + s], g[2], fmaf(wre[64 + s], g[1], wre[s] * g[0]));
                 if (s < 12) {
                     const int j = q * 12 + s, d = j >> 4, k = (j & 15) >> 1, ph = j & 1;
-                    const float cs = cosf(freq_arg(x[d], k, ph)) * ldexpf(3.14159274101257324f, k) * de;
+                    const float cs = cos_reduced(freq_arg(x[d], k, ph)) * ldexpf(3.14159274101257324f, k) * de;
                     if (d == 0) dx[0] += cs; else if (d == 1) dx[1] += cs; else dx[2] += cs;
                 } else if (q == 0 && s < 15) {
                     dx[s - 12] += de;

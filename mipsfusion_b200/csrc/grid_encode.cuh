@@ -38,32 +38,50 @@ __device__ __forceinline__ void pos_fract(float x, float scale, uint32_t& cell, 
     frac = pos - fl;
 }
 
-__device__ __forceinline__ float corner_weight(int c, const float f[3]) {
-    float w = 1.0f;
+// The 8 corner indices and trilinear weights of one level.  Same arithmetic as grid_index / the tcnn corner loop
+// (uint32 wrap-around; weight = ((1 * w_x) * w_y) * w_z), with the per-dimension terms computed once.  Hashed
+// levels always have a power-of-two size (2^log2_hashmap_size), so their modulo is a mask.
+__device__ __forceinline__ void grid_corners(const float x[3], const LevelInfo& li, uint32_t (&idx)[8], float (&w)[8]) {
+    uint32_t g[3]; float f[3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) w = __fmul_rn(w, ((c >> d) & 1) ? f[d] : __fsub_rn(1.0f, f[d]));
-    return w;
+    for (int d = 0; d < 3; ++d) pos_fract(x[d], li.scale, g[d], f[d]);
+    uint32_t tx[2], ty[2], tz[2];
+    tx[0] = g[0]; tx[1] = g[0] + 1u;
+    if (li.hashed) {
+        ty[0] = g[1] * MF_PRIME1; ty[1] = (g[1] + 1u) * MF_PRIME1;
+        tz[0] = g[2] * MF_PRIME2; tz[1] = (g[2] + 1u) * MF_PRIME2;
+        const uint32_t mask = li.size - 1u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) idx[c] = (tx[c & 1] ^ ty[(c >> 1) & 1] ^ tz[(c >> 2) & 1]) & mask;
+    } else {
+        const uint32_t r2 = li.res * li.res;
+        ty[0] = g[1] * li.res; ty[1] = (g[1] + 1u) * li.res;
+        tz[0] = g[2] * r2; tz[1] = (g[2] + 1u) * r2;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint32_t i = tx[c & 1] + ty[(c >> 1) & 1] + tz[(c >> 2) & 1];
+            if (i >= li.size) i %= li.size;
+            idx[c] = i;
+        }
+    }
+    const float wx[2] = {__fsub_rn(1.0f, f[0]), f[0]}, wy[2] = {__fsub_rn(1.0f, f[1]), f[1]}, wz[2] = {__fsub_rn(1.0f, f[2]), f[2]};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) w[c] = __fmul_rn(__fmul_rn(wx[c & 1], wy[(c >> 1) & 1]), wz[(c >> 2) & 1]);
 }
 
 // Forward gather of one level: 8 corners, 2 features.  idx_out (8) optional.
 __device__ __forceinline__ float2 grid_level_fwd(const float x[3], const float2* __restrict__ grid2,
                                                  const LevelInfo& li, uint32_t* idx_out) {
-    uint32_t g[3]; float f[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) pos_fract(x[d], li.scale, g[d], f[d]);
-    uint32_t idx[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-        idx[c] = grid_index(g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + ((c >> 2) & 1), li);
+    uint32_t idx[8]; float w[8];
+    grid_corners(x, li, idx, w);
     float2 v[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) v[c] = __ldg(&grid2[li.offset + idx[c]]);     // 8 independent gathers in flight
     float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        float w = corner_weight(c, f);
-        acc.x = fmaf(w, v[c].x, acc.x);
-        acc.y = fmaf(w, v[c].y, acc.y);
+        acc.x = fmaf(w[c], v[c].x, acc.x);
+        acc.y = fmaf(w[c], v[c].y, acc.y);
         if (idx_out) idx_out[c] = idx[c];
     }
     return acc;
@@ -78,21 +96,16 @@ __device__ __forceinline__ void red_add_f2(float* addr, float a, float b) {
 template <bool WANT_DX>
 __device__ __forceinline__ void grid_level_bwd(const float x[3], float2 dy, const float2* __restrict__ grid2,
                                                float* __restrict__ grad, const LevelInfo& li, float dx[3]) {
-    uint32_t g[3]; float f[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) pos_fract(x[d], li.scale, g[d], f[d]);
-    uint32_t idx[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-        idx[c] = grid_index(g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + ((c >> 2) & 1), li);
+    uint32_t idx[8]; float w8[8];
+    grid_corners(x, li, idx, w8);
     if (dy.x != 0.f || dy.y != 0.f) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float w = corner_weight(c, f);
-            red_add_f2(grad + 2 * (size_t)(li.offset + idx[c]), w * dy.x, w * dy.y);
-        }
+        for (int c = 0; c < 8; ++c) red_add_f2(grad + 2 * (size_t)(li.offset + idx[c]), w8[c] * dy.x, w8[c] * dy.y);
     }
     if (WANT_DX) {
+        float f[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { uint32_t gd; pos_fract(x[d], li.scale, gd, f[d]); }
         float2 v[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) v[c] = __ldg(&grid2[li.offset + idx[c]]);
@@ -130,4 +143,22 @@ __device__ __forceinline__ void prenormalized_point(const FieldDev& f, const flo
 __device__ __forceinline__ float freq_arg(float x, int k, int s) {
     float a = __fmul_rn(ldexpf(x, k), 3.14159274101257324f);
     return s ? __fadd_rn(a, 1.57079637050628662f) : a;
+}
+
+// sin(arg) for the tensor-core kernels: explicit three-term Cody-Waite reduction to [-pi, pi] followed by the
+// MUFU approximation (abs error ~5e-7 for |arg| <= 128 pi + pi/2, the range of the frequency encoding).  The
+// argument is the same fp32 number the oracle feeds to torch.sin; only the evaluation is cheaper than sinf().
+__device__ __forceinline__ float sin_reduced(float arg) {
+    const float k = rintf(arg * 0.15915494309189535f);
+    float r = fmaf(k, -6.28318548202514648f, arg);          // 2 pi = hi + mid + lo
+    r = fmaf(k, 1.74845553146951715e-7f, r);
+    r = fmaf(k, 7.1054274e-15f, r);
+    return __sinf(r);
+}
+__device__ __forceinline__ float cos_reduced(float arg) {
+    const float k = rintf(arg * 0.15915494309189535f);
+    float r = fmaf(k, -6.28318548202514648f, arg);
+    r = fmaf(k, 1.74845553146951715e-7f, r);
+    r = fmaf(k, 7.1054274e-15f, r);
+    return __cosf(r);
 }

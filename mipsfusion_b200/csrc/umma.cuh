@@ -145,10 +145,12 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4])
 
 // ---- bf16 hi/lo split: x ~= hi + lo with |x - hi - lo| <= 2^-17 |x| --------------------------
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-    const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-    hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);   // element 2c in the low half
-    lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+    // packed conversions: one cvt.rn.bf16x2.f32 per pair (element 2c in the low half)
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 }  // namespace umma
@@ -194,7 +196,8 @@ __device__ __forceinline__ uint64_t desc_mn(const uint8_t* tile, int row0, uint3
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 }  // namespace umma
