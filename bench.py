@@ -259,6 +259,7 @@ def run_gpu(args):
     also = {}
     if world == 1:
         also = tracking_bench(model, cfg, dev)
+        also.update(frame_bench(dev))
 
     if rank != 0:
         if world > 1:
@@ -269,8 +270,11 @@ def run_gpu(args):
     P = R_RAYS * S
     bwd_ms = phase_ms.get("field_bwd", float("nan"))
     achieved = ALG_BYTES_PER_POINT_BWD * P / (bwd_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "field_bwd_kernel (recompute-forward + decoder backward + grid scatter)",
-            "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+    roof = {"bound": "hbm", "kernel": "field_bwd_tc_kernel (tcgen05 recompute-forward + dgrad + wgrad + grid scatter)",
+            "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, ncu --set full
+            # (profiles/r1_tc_summary.md): 96.77 MB + 26.78 MB; below the algorithmic bytes because the table is L2 resident
+            "traffic": 123.55e6, "traffic_unit": "bytes/launch",
             "peak_source": which, "ms_per_launch": bwd_ms, "alg_bytes_per_launch": ALG_BYTES_PER_POINT_BWD * P,
             "phase_ms": phase_ms,
             "adam_gbs": ADAM_BYTES_PER_PARAM * (9014144 + 36577) / (phase_ms.get("adam", float("nan")) * 1e-3) / 1e9,
@@ -345,6 +349,67 @@ def emit(obj):
 
 
 _REAL_STDOUT = 1
+
+def frame_bench(dev, frames=3):
+    """ms/frame of the reference's per-frame work at its shipped sizes (configs/FastCaMo-synth/FastCaMo-synth.yaml):
+    RandomOptimizer 5 iterations x 2000 particles x 384 pixels, 10 gradient pose-refinement iterations x 1000 rays x 75
+    samples (pose gradients -> fp32 decoder route), and 15 mapping iterations x 2600 rays x 75 samples every 3rd frame
+    (amortised), on one synthetic 640x480 frame (cropped to 620x460)."""
+    import types
+    import torch
+    import helpers as H
+    import mipsfusion_b200 as mf
+    from mipsfusion_b200 import synth
+    from mipsfusion_b200.mapper import FusedMapper
+    from mipsfusion_b200 import sampling_helper as sh
+    cfg = H.make_config(HASH, n_samples_d=50, n_range_d=25)
+    cfg["tracking"] = {"RO": {"particle_size": 2000, "initial_scaling_factor": 0.02, "rescaling_factor": 0.5, "n_rows": 16, "n_cols": 24},
+                       "ignore_edge_W": 20, "ignore_edge_H": 20}
+    of = H.oracle_field(cfg)
+    model = H.cuda_model(cfg, H.state_of(of))
+    dirs = synth.camera_rays()
+    c2w = synth.trajectory(4)[1]
+    frame = synth.render_frame(c2w, dirs)
+    depth_d, rgb_d, dirs_d = frame["depth"].to(dev), frame["rgb"].to(dev), dirs.to(dev)
+    ds = types.SimpleNamespace(H=460, W=620, fx=320.0, fy=320.0, cx=309.5, cy=229.5, rays_d=dirs)
+    ro = mf.RandomOptimizer(cfg, types.SimpleNamespace(dataset=ds, device=str(dev)))
+    mapper = FusedMapper(model)
+    tw = cfg["training"]
+
+    def one_frame(do_map):
+        model.eval()
+        pose = ro.optimize(model, frame["depth"], c2w.clone(), c2w.clone(), n_iter=5).to(dev)      # RO (returns a CPU pose, as the reference)
+        model.train()
+        rows, cols = sh.sample_pixels_mix(460, 620, 16, 24, depth_d, 1000)
+        d_cam, t_rgb, t_d = dirs_d[rows, cols], rgb_d[rows, cols], depth_d[rows, cols].unsqueeze(-1)
+        trans = pose[:3, 3].clone().requires_grad_(True)
+        rot = pose[:3, :3].clone().requires_grad_(True)
+        opt = torch.optim.Adam([rot, trans], lr=1e-3)
+        for _ in range(10):                                                                       # GO (mipsfusion.py:501-556)
+            opt.zero_grad()
+            rays_o = trans[None, :].repeat(1000, 1)
+            rays_d = torch.sum(d_cam[..., None, :] * rot[None], -1)
+            ret = model(rays_o, rays_d, t_rgb, t_d, EMD_w=0.0)
+            loss = tw["rgb_weight"] * ret["rgb_loss"] + tw["sdf_weight"] * ret["sdf_loss"] + tw["fs_weight"] * ret["fs_loss"]
+            loss.backward()
+            opt.step()
+        if do_map:
+            idx = torch.randint(0, 460 * 620, (2600,), device=dev)
+            r_, c_ = idx // 620, idx % 620
+            ro_, rd_ = pose[None, :3, 3].repeat(2600, 1).contiguous(), torch.sum(dirs_d[r_, c_][..., None, :] * pose[None, :3, :3], -1).contiguous()
+            for _ in range(15):                                                                   # local BA (mipsfusion.py:293-335)
+                mapper.step(ro_, rd_, rgb_d[r_, c_].contiguous(), depth_d[r_, c_].contiguous())
+        return float(loss.detach())
+    one_frame(True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(frames):
+        one_frame(k % 3 == 0)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / frames * 1e3
+    return {"ms_per_frame_640x480": ms,
+            "frame_shape": "RO 5 x 2000 x 384, pose refinement 10 x 1000 rays x 75 (fp32 decoder route), mapping 15 x 2600 rays x 75 every 3rd frame"}
+
 
 if __name__ == "__main__":
     sys.stdout.flush()
