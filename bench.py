@@ -260,6 +260,7 @@ def run_gpu(args):
     if world == 1:
         also = tracking_bench(model, cfg, dev)
         also.update(frame_bench(dev))
+        also.update(joint_query_bench(dev))
 
     if rank != 0:
         if world > 1:
@@ -349,6 +350,41 @@ def emit(obj):
 
 
 _REAL_STDOUT = 1
+
+def joint_query_bench(dev, res=512, n_submaps=16):
+    """BASELINE configs[4] shape: joint SDF grid query at res^3 over n_submaps submaps (Mesher / render_mesh path):
+    containment + world->submap transform + field query (sdf, entropy) + entropy/distance-weighted blend."""
+    import numpy as np
+    import torch
+    import helpers as H
+    import mipsfusion_b200 as mf
+    cfg = H.make_config(HASH)
+    cfg["grid"]["use_bound_normalize"] = False
+    of = H.oracle_field(cfg)
+    state = H.state_of(of)
+    models, poses, amin, amax, cents = [], [], [], [], []
+    lo, hi = np.array([-0.6, 0.5, -1.15]), np.array([2.95, 7.05, 3.05])
+    ext = hi - lo
+    for m in range(n_submaps):                                   # 4 x 4 overlapping boxes across x / y, full height
+        ix, iy = m % 4, m // 4
+        a = lo + ext * np.array([ix / 4.0 - 0.08, iy / 4.0 - 0.08, 0.0])
+        b = lo + ext * np.array([(ix + 1) / 4.0 + 0.08, (iy + 1) / 4.0 + 0.08, 1.0])
+        models.append(H.cuda_model(cfg, state, train=False))
+        T = torch.eye(4); T[:3, 3] = torch.tensor((a + b) / 2, dtype=torch.float32)
+        poses.append(T); amin.append(a); amax.append(b); cents.append(((a + b) / 2).astype(np.float32))
+    axes = [np.linspace(lo[k], hi[k], res) for k in range(3)]
+    jq = mf.JointSubmapQuery(models, poses, amin, amax, cents)
+    jq.query(axes=[a_[:64] for a_ in axes])                      # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = jq.query(axes=axes)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    frac = float(out["mask"].float().mean())
+    del out
+    return {"joint_query_grid_points_per_s": res ** 3 / dt, "joint_query_s": dt,
+            "joint_query_shape": f"{res}^3 grid x {n_submaps} submaps (T=2^{HASH} each), {frac:.2f} of the points inside >= 1 submap"}
+
 
 def frame_bench(dev, frames=3):
     """ms/frame of the reference's per-frame work at its shipped sizes (configs/FastCaMo-synth/FastCaMo-synth.yaml):
