@@ -196,6 +196,10 @@ int mf_sample_pixels_topk(const float* depth, const float* keys, int img_h, int 
  * dirs_cam (R,3); poses (K,4,4) c2w; pose_idx (R) int64 or NULL (=> pose 0) -> rays_o, rays_d (R,3). */
 int mf_gen_rays(const float* dirs_cam, const float* poses, const int64_t* pose_idx, float* rays_o, float* rays_d,
                 int64_t R, int K, void* stream);
+/* The same on the packed host batch of the mapping loop (mipsfusion.py:289-290,310-322): rays7 (R,7) =
+ * [dir_cam | rgb | depth] -> rays_o, rays_d, target_rgb (R,3), target_d (R). */
+int mf_gen_rays_packed(const float* rays7, const float* poses, const int64_t* pose_idx, float* rays_o, float* rays_d,
+                       float* target_rgb, float* target_d, int64_t R, int K, void* stream);
 /* d_poses (K,4,4) += backward of mf_gen_rays (rotation block and translation column). */
 int mf_gen_rays_bwd(const float* dirs_cam, const int64_t* pose_idx, const float* d_rays_o, const float* d_rays_d,
                     float* d_poses, int64_t R, int K, void* stream);

@@ -341,15 +341,19 @@ __global__ void __launch_bounds__(256) render_loss_bwd_kernel(
 // ---------------------------------------------------------------------------------------------
 // Ray generation (camera -> submap frame) and its backward to the poses.
 // ---------------------------------------------------------------------------------------------
-__global__ void gen_rays_kernel(const float* __restrict__ dirs, const float* __restrict__ poses,
+// ld = floats per input record: 3 for a (R,3) direction array, 7 for the packed ray record [dir_cam | rgb | depth]
+// of the keyframe ray store (mipsfusion.py:289-290,316-318), whose colour / depth columns are split out as well.
+__global__ void gen_rays_kernel(const float* __restrict__ dirs, int ld, const float* __restrict__ poses,
                                 const int64_t* __restrict__ pose_idx, float* __restrict__ rays_o,
-                                float* __restrict__ rays_d, int64_t R, int K) {
+                                float* __restrict__ rays_d, float* __restrict__ rgb, float* __restrict__ depth, int64_t R, int K) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     int64_t pi = pose_idx ? pose_idx[r] : 0;
     if (pi < 0) pi += K;                                        // python negative indexing (mipsfusion.py:313)
     const float* P = poses + pi * 16;
-    const float dx = dirs[r * 3], dy = dirs[r * 3 + 1], dz = dirs[r * 3 + 2];
+    const float dx = dirs[r * ld], dy = dirs[r * ld + 1], dz = dirs[r * ld + 2];
+    if (rgb) { rgb[r * 3] = dirs[r * ld + 3]; rgb[r * 3 + 1] = dirs[r * ld + 4]; rgb[r * 3 + 2] = dirs[r * ld + 5]; }
+    if (depth) depth[r] = dirs[r * ld + 6];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         // torch.sum(d[..., None, :] * R, -1): three products, then summed
@@ -436,7 +440,19 @@ MF_API int mf_gen_rays(const float* dirs_cam, const float* poses, const int64_t*
     MF_CHECK_ARG(R >= 0 && K >= 1);
     if (R == 0) return MF_OK;
     MF_CHECK_ARG(dirs_cam && poses && rays_o && rays_d);
-    gen_rays_kernel<<<(unsigned)((R + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dirs_cam, poses, pose_idx, rays_o, rays_d, R, K);
+    gen_rays_kernel<<<(unsigned)((R + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dirs_cam, 3, poses, pose_idx, rays_o, rays_d,
+                                                                                   nullptr, nullptr, R, K);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}
+
+MF_API int mf_gen_rays_packed(const float* rays7, const float* poses, const int64_t* pose_idx, float* rays_o, float* rays_d,
+                              float* target_rgb, float* target_d, int64_t R, int K, void* stream) {
+    MF_CHECK_ARG(R >= 0 && K >= 1);
+    if (R == 0) return MF_OK;
+    MF_CHECK_ARG(rays7 && poses && rays_o && rays_d && target_rgb && target_d);
+    gen_rays_kernel<<<(unsigned)((R + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rays7, 7, poses, pose_idx, rays_o, rays_d,
+                                                                                   target_rgb, target_d, R, K);
     MF_LAUNCH_CHECK();
     return MF_OK;
 }

@@ -109,6 +109,32 @@ class FusedMapper:
                 tm.setdefault(name, []).append((a, c))
         return b["losses"]
 
+    def step_host(self, rays7, pose_idx, poses, EMD_w=0.01):
+        """One mapping iteration from the HOST batch of the reference's BA loop (mipsfusion.py:289-322):
+        ``rays7`` (R,7) float32 host tensor [dir_cam | rgb | depth] (pinned memory makes the copy asynchronous),
+        ``pose_idx`` (R,) int64 host tensor (keyframe slot of each ray, -1 = current frame = last pose) or None,
+        ``poses`` (K,4,4) camera-to-submap poses on the device.  Copies the batch to the device, generates the rays,
+        runs :meth:`step` and returns the 8 loss terms as a host tensor (one synchronisation)."""
+        R = rays7.shape[0]
+        hb = self._bufs.get(("host", R))
+        if hb is None:
+            f32 = dict(device=self.dev, dtype=torch.float32)
+            hb = dict(rays7=torch.empty(R, 7, **f32), idx=torch.empty(R, device=self.dev, dtype=torch.int64),
+                      o=torch.empty(R, 3, **f32), d=torch.empty(R, 3, **f32), rgb=torch.empty(R, 3, **f32),
+                      depth=torch.empty(R, **f32), out=torch.empty(8, dtype=torch.float32).pin_memory())
+            self._bufs[("host", R)] = hb
+        hb["rays7"].copy_(rays7, non_blocking=True)
+        if pose_idx is not None:
+            hb["idx"].copy_(pose_idx, non_blocking=True)
+        poses = poses.contiguous()
+        L.call("mf_gen_rays_packed", L.ptr(hb["rays7"]), L.ptr(poses), L.ptr(hb["idx"]) if pose_idx is not None else None,
+               L.ptr(hb["o"]), L.ptr(hb["d"]), L.ptr(hb["rgb"]), L.ptr(hb["depth"]), R, poses.shape[0], L.stream())
+        self.launches += 1
+        losses = self.step(hb["o"], hb["d"], hb["rgb"], hb["depth"], EMD_w=EMD_w)
+        hb["out"].copy_(losses, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return hb["out"]
+
     def apply_gradients(self):
         """Adam on (grid, decoder) with the reference's groups (mipsfusion.py:580-584), zero_grad fused in."""
         self.step_count += 1

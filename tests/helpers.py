@@ -60,8 +60,10 @@ def rel_err(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
 
 
-def synth_batch(R, S, seed=0, invalid=3):
-    """Rays from a synthetic SDF-room frame: rays_o, rays_d, rgb, depth (R,1), u (R,S)."""
+def synth_batch_packed(R, seed=0, invalid=3):
+    """The host batch of the reference's mapping loop (mipsfusion.py:289-318) from a synthetic SDF-room frame:
+    rays7 (R,7) = [dir_cam | rgb | depth], pose_idx (R,) int64 (all -1: the current frame), poses (1,4,4), and the
+    generator used (for further draws)."""
     from mipsfusion_b200 import synth
     g = torch.Generator().manual_seed(seed)
     c2w = synth.trajectory(4)[1]
@@ -74,6 +76,13 @@ def synth_batch(R, S, seed=0, invalid=3):
     rays = rays[sel].clone()
     assert rays.shape[0] == R, (rays.shape, R)
     rays[:invalid, 6] = 0.0
+    return rays.contiguous(), -torch.ones(R, dtype=torch.int64), c2w[None].contiguous(), g
+
+
+def synth_batch(R, S, seed=0, invalid=3):
+    """Rays from a synthetic SDF-room frame: rays_o, rays_d, rgb, depth (R,1), u (R,S)."""
+    rays, _, poses, g = synth_batch_packed(R, seed, invalid)
+    c2w = poses[0]
     rays_d = torch.sum(rays[:, None, :3] * c2w[None, :3, :3], -1)
     rays_o = c2w[None, :3, 3].repeat(R, 1)
     u = torch.rand(R, S, generator=g)
