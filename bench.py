@@ -281,13 +281,22 @@ def run_gpu(args):
     hbm, tf, which = peaks()
     P = R_RAYS * S
     bwd_ms = phase_ms.get("field_bwd", float("nan"))
-    achieved = ALG_BYTES_PER_POINT_BWD * P / (bwd_ms * 1e-3) / 1e9
+    # points whose upstream gradient row is non-zero: the only ones the backward has to visit (the kernel skips the rest)
+    d_raw = mapper._bufs[(R_RAYS, S)]["d_raw"]
+    n_active = int((d_raw.view(-1, d_raw.shape[-1]) != 0).any(-1).sum())
+    alg_bytes = ALG_BYTES_PER_POINT_BWD * n_active + 4 * d_raw.shape[-1] * P      # table traffic of the active points + d_raw of all
+    achieved = alg_bytes / (bwd_ms * 1e-3) / 1e9
+    achieved_all = ALG_BYTES_PER_POINT_BWD * P / (bwd_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "field_bwd_tc_kernel (tcgen05 recompute-forward + dgrad + wgrad + grid scatter)",
             "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, ncu --set full
             # (profiles/r1_tc_summary.md): 96.77 MB + 26.78 MB; below the algorithmic bytes because the table is L2 resident
             "traffic": 123.55e6, "traffic_unit": "bytes/launch",
-            "peak_source": which, "ms_per_launch": bwd_ms, "alg_bytes_per_launch": ALG_BYTES_PER_POINT_BWD * P,
+            "peak_source": which, "ms_per_launch": bwd_ms, "alg_bytes_per_launch": alg_bytes,
+            "points_per_launch": P, "active_points_per_launch": n_active,
+            "note": "achieved counts 2,048 B for the ACTIVE points only (+ 40 B of d_raw for every point); with SURVEY 8d's "
+                    "2,048 B x all points the same launch reads as achieved_all_points",
+            "achieved_all_points": achieved_all, "frac_all_points": achieved_all / hbm,
             "phase_ms": phase_ms,
             "adam_gbs": ADAM_BYTES_PER_PARAM * (9014144 + 36577) / (phase_ms.get("adam", float("nan")) * 1e-3) / 1e9,
             "fwd_gbs": ALG_BYTES_PER_POINT_FWD * P / (phase_ms.get("field_fwd", float("nan")) * 1e-3) / 1e9}

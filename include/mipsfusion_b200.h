@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MF_ABI_VERSION 1
+#define MF_ABI_VERSION 2
 #define MF_MAX_LEVELS 16
 #define MF_MLP_PARAMS 36577          /* reference model/decoder.py:32-50 with input_ch=32, input_ch_pos=48 */
 #define MF_RAW_DIM 10                /* rgb_raw(3) sdf(1) entropy(1) prob(5), model/decoder.py:74 */
@@ -131,7 +131,10 @@ int mf_mlp_bwd(const float* embed, const float* embed_pos, const float* pts, con
  * pts (N,3) fp32 in the submap frame -> out (N,10).  normalize=0 skips the bound normalisation
  * (query_color_sdf called directly on pre-normalised points, as model/Mesher.py:487 does). */
 int mf_field_query(const float* pts, const mf_field* field_host, int normalize, float* out, int64_t N, void* stream);
-/* backward of the above: grad_grid/grad_mlp accumulate; d_pts (N,3) optional. */
+/* backward of the above: grad_grid/grad_mlp accumulate; d_pts (N,3) optional.
+ * workspace: mf_field_bwd_workspace_size(N, 0) floats (per-CTA partial sums + the list of points whose d_out row is
+ * non-zero: rows that are exactly zero add nothing to any gradient and are skipped). */
+int64_t mf_field_bwd_workspace_size(int64_t n_points, int want_ray_grads);
 int mf_field_query_bwd(const float* pts, const mf_field* field_host, int normalize, const float* d_out,
                        float* grad_grid, float* grad_mlp, float* d_pts, float* workspace, int64_t N, void* stream);
 
@@ -152,7 +155,8 @@ int mf_sample_z(const float* target_d, const float* u, const float* lin_uniform,
 int64_t mf_feat_cache_size(int64_t n_points);
 int mf_field_query_rays(const float* rays_o, const float* rays_d, const float* z, const mf_field* field_host,
                         float* raw, void* feat, int64_t R, int S, void* stream);
-/* d_raw (R,S,10) -> grad_grid, grad_mlp (accumulate), d_rays_o / d_rays_d (R,3; optional, overwritten). */
+/* d_raw (R,S,10) -> grad_grid, grad_mlp (accumulate), d_rays_o / d_rays_d (R,3; optional, overwritten).
+ * workspace: mf_field_bwd_workspace_size(R*S, d_rays_o != NULL) floats. */
 int mf_field_query_rays_bwd(const float* rays_o, const float* rays_d, const float* z, const mf_field* field_host,
                             const float* d_raw, const void* feat, float* grad_grid, float* grad_mlp, float* d_rays_o,
                             float* d_rays_d, float* workspace, int64_t R, int S, void* stream);

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "mf_mlp_prep_size": (_L, []),
     "mf_mlp_prepare": (_I, [_P, _P, _P]),
     "mf_mlp_fwd": (_I, [_P, _P, _P, _P, _P, _L, _P]),
+    "mf_field_bwd_workspace_size": (_L, [_L, _I]),
     "mf_mlp_grad_workspace_size": (_L, []),
     "mf_mlp_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
     "mf_field_query": (_I, [_P, C.POINTER(Field), _I, _P, _L, _P]),

@@ -5,15 +5,17 @@
 
 // Head backward for point m (threads 0..TP-1): d_raw (10) + forward OUT rows -> DZ rows
 // (dlogits 0..4, drgb_raw 5..7).   model/decoder.py:65-74 differentiated.
-__device__ __forceinline__ void head_backward_tile(const float* __restrict__ d_raw, int64_t tile, int64_t N, float* sm) {
+__device__ __forceinline__ void head_backward_tile(const float* __restrict__ d_raw, int64_t tile, int64_t N, float* sm,
+                                                   const ActiveMap am = ActiveMap{nullptr, nullptr}) {
     const int m = threadIdx.x;
     if (m >= TP) return;
     const float* OUT = sm + ROW_OUT * LDA;
     float* DZ = sm + ROW_DZ * LDA;
-    const int64_t i = tile * TP + m;
+    const int64_t slot = tile * TP + m;
+    const int64_t i = slot < N ? am(slot) : 0;
     float g[MF_RAW_DIM];
 #pragma unroll
-    for (int c = 0; c < MF_RAW_DIM; ++c) g[c] = (i < N) ? d_raw[i * MF_RAW_DIM + c] : 0.f;
+    for (int c = 0; c < MF_RAW_DIM; ++c) g[c] = (slot < N) ? d_raw[i * MF_RAW_DIM + c] : 0.f;
     float p[N_CLASS], dp[N_CLASS], dot = 0.f;
 #pragma unroll
     for (int c = 0; c < N_CLASS; ++c) {
@@ -173,10 +175,12 @@ __device__ __forceinline__ void mlp_backward_tile(const float* __restrict__ prep
 template <class Src, bool WANT_DX>
 __device__ __forceinline__ void encode_backward_tile(const FieldDev& f, const Src& src, int64_t tile, int64_t N,
                                                      float* sm, float* __restrict__ grad_grid,
-                                                     float* __restrict__ d_pts) {
+                                                     float* __restrict__ d_pts,
+                                                     const ActiveMap am = ActiveMap{nullptr, nullptr}) {
     const int tid = threadIdx.x, m = tid & (TP - 1), q = tid >> 6;
-    const int64_t i = tile * TP + m;
-    const bool valid = i < N;
+    const int64_t slot = tile * TP + m;
+    const bool valid = slot < N;
+    const int64_t i = valid ? am(slot) : 0;
     float* E = sm + ROW_E * LDA; float* G = sm + ROW_G * LDA; float* PS = sm + ROW_SM * LDA;
     float x[3] = {0.f, 0.f, 0.f};
     if (valid) src.point(i, f, x);

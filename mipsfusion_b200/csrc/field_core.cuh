@@ -59,10 +59,12 @@ struct SrcRays {                         // pts = rays_o + rays_d * z   (model/s
 // outputs of point m.
 // ------------------------------------------------------------------------------------------
 template <class Src>
-__device__ __forceinline__ void encode_tile(const FieldDev& f, const Src& src, int64_t tile, int64_t N, float* sm) {
+__device__ __forceinline__ void encode_tile(const FieldDev& f, const Src& src, int64_t tile, int64_t N, float* sm,
+                                            const ActiveMap am = ActiveMap{nullptr, nullptr}) {
     const int tid = threadIdx.x, m = tid & (TP - 1), q = tid >> 6;
-    const int64_t i = tile * TP + m;
-    const bool valid = i < N;
+    const int64_t slot = tile * TP + m;
+    const bool valid = slot < N;
+    const int64_t i = valid ? am(slot) : 0;
     float x[3] = {0.f, 0.f, 0.f};
     if (valid) src.point(i, f, x);
     float* E = sm + ROW_E * LDA;

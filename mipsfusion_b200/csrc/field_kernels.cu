@@ -99,21 +99,22 @@ __global__ void __launch_bounds__(NT, 2) mlp_fwd_kernel(const float* embed, cons
 template <class Src, bool WANT_DX>
 __global__ void __launch_bounds__(NT, 1) field_bwd_kernel(FieldDev f, Src src, const float* __restrict__ d_raw,
                                                           float* __restrict__ grad_grid, float* __restrict__ part,
-                                                          float* __restrict__ d_pts, int64_t N) {
+                                                          float* __restrict__ d_pts, int64_t N_all, ActiveMap am) {
     extern __shared__ __align__(16) float sm[];
     float* gpart = part + (size_t)blockIdx.x * MF_MLP_PARAMS;
     for (int i = threadIdx.x; i < MF_MLP_PARAMS; i += NT) gpart[i] = 0.f;
     __syncthreads();
+    const int64_t N = am.n(N_all);                     // active points only
     const int64_t n_tiles = (N + TP - 1) / TP;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        encode_tile(f, src, tile, N, sm);
+        encode_tile(f, src, tile, N, sm, am);
         __syncthreads();
         mlp_forward_tile<false>(f.prep, sm, sm + ROW_H3 * LDA);
         __syncthreads();
-        head_backward_tile(d_raw, tile, N, sm);
+        head_backward_tile(d_raw, tile, N, sm, am);
         __syncthreads();
         mlp_backward_tile<WANT_DX>(f.prep, sm, gpart);
-        encode_backward_tile<Src, WANT_DX>(f, src, tile, N, sm, grad_grid, d_pts);
+        encode_backward_tile<Src, WANT_DX>(f, src, tile, N, sm, grad_grid, d_pts, am);
         __syncthreads();
     }
 }
@@ -153,20 +154,33 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const float* embed, cons
     }
 }
 
-// grad_mlp[i] += sum over CTAs of part[cta][i]  (fixed order -> deterministic)
-// transposed != 0: the three 128-row weight matrices are stored [in][out] inside each partial (tensor-core path)
-__global__ void reduce_partials_kernel(const float* __restrict__ part, int n_cta, float* __restrict__ grad_mlp, int transposed) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= MF_MLP_PARAMS) return;
-    int src = i;
-    if (transposed) {
-        if (i < OFF_B1) { const int n = i / D_E, k = i % D_E; src = OFF_W1 + k * D_H + n; }
-        else if (i >= OFF_W2 && i < OFF_B2) { const int r = i - OFF_W2; src = OFF_W2 + (r % D_H) * D_H + r / D_H; }
-        else if (i >= OFF_WS1 && i < OFF_BS1) { const int r = i - OFF_WS1; src = OFF_WS1 + (r % D_SDF_IN) * D_H + r / D_SDF_IN; }
-    }
+// grad_mlp[dst(s)] += sum over CTAs of part[cta][s].  A block covers 32 consecutive partial entries s; warp j sums the
+// CTAs j, j+8, ... in order (coalesced 128-byte reads), then the 8 partial sums are combined in a fixed order ->
+// deterministic.  transposed != 0: the three 128-row weight matrices are stored [in][out] inside each partial
+// (tensor-core path) and dst() undoes that.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int n_cta, float* __restrict__ grad_mlp,
+                                                              int transposed) {
+    __shared__ float acc[8][32];
+    const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
+    const int sidx = blockIdx.x * 32 + lane;
+    const bool on = sidx < MF_MLP_PARAMS;
     float s = 0.f;
-    for (int c = 0; c < n_cta; ++c) s += part[(size_t)c * MF_MLP_PARAMS + src];
-    grad_mlp[i] += s;
+    if (on) {
+#pragma unroll 4
+        for (int c = j; c < n_cta; c += 8) s += __ldg(&part[(size_t)c * MF_MLP_PARAMS + sidx]);
+    }
+    acc[j][lane] = s;
+    __syncthreads();
+    if (j == 0 && on) {
+        const float tot = ((acc[0][lane] + acc[1][lane]) + (acc[2][lane] + acc[3][lane])) + ((acc[4][lane] + acc[5][lane]) + (acc[6][lane] + acc[7][lane]));
+        int dst = sidx;
+        if (transposed) {
+            if (sidx < OFF_B1) { const int r = sidx - OFF_W1; dst = OFF_W1 + (r % D_H) * D_E + r / D_H; }
+            else if (sidx >= OFF_W2 && sidx < OFF_B2) { const int r = sidx - OFF_W2; dst = OFF_W2 + (r % D_H) * D_H + r / D_H; }
+            else if (sidx >= OFF_WS1 && sidx < OFF_BS1) { const int r = sidx - OFF_WS1; dst = OFF_WS1 + (r % D_H) * D_SDF_IN + r / D_H; }
+        }
+        grad_mlp[dst] += tot;
+    }
 }
 
 // d_rays_o[r] = sum_s d_pts[r,s]; d_rays_d[r] = sum_s z[r,s] d_pts[r,s]   (warp per ray, fixed order)
@@ -269,6 +283,8 @@ int mf_field_to_dev(const mf_field* f, FieldDev* d) {
     d->tc_img = reinterpret_cast<const uint8_t*>(f->mlp_prep + PREP_TC);
     for (int k = 0; k < 3; ++k) { d->na[k] = f->norm_a[k]; d->nb[k] = f->norm_b[k]; }
     d->nf = f->norm_factor;
+    for (int l = 0; l < f->meta.n_levels; ++l)
+        if (f->meta.offset[l] & 1u) { mf_set_error("mf_field: level offsets must be even (16-byte reductions)"); return MF_ERR_INVALID; }
     d->impl = f->decoder_impl == 0 ? mf_decoder_impl() : (f->decoder_impl == 1 ? 1 : 0);
     d->n_levels = f->meta.n_levels;
     for (int l = 0; l < MF_MAX_LEVELS; ++l) {
@@ -338,7 +354,9 @@ MF_API int mf_hashgrid_bwd(const float* x, const float* dL_dy, const float* grid
     MF_CHECK_ARG(N >= 0);
     if (N == 0) return MF_OK;
     MF_CHECK_ARG(x && dL_dy && grid && grad_grid);
+    MF_CHECK_ARG(((uintptr_t)grad_grid & 15) == 0);          // the scatter uses 16-byte reductions
     FieldDev d; int rc = meta_to_dev(meta, grid, &d); if (rc) return rc;
+    for (int l = 0; l < d.n_levels; ++l) MF_CHECK_ARG((d.offset[l] & 1u) == 0);
     if (dL_dx && d.n_levels != 16) { mf_set_error("mf_hashgrid_bwd: input gradient needs 16 levels"); return MF_ERR_UNSUPPORTED; }
     const int64_t T = N * d.n_levels;
     const unsigned blocks = (unsigned)((T + 255) / 256);
@@ -410,40 +428,127 @@ MF_API int mf_mlp_bwd(const float* embed, const float* embed_pos, const float* p
         mlp_bwd_kernel<false><<<grid, NT, SMEM_BWD, st>>>(embed, embed_pos, pts, mlp_prep, d_out, workspace, d_embed, nullptr, nullptr, N);
     }
     MF_LAUNCH_CHECK();
-    reduce_partials_kernel<<<(MF_MLP_PARAMS + 255) / 256, 256, 0, st>>>(workspace, grid, grad_mlp, 0);
+    reduce_partials_kernel<<<(MF_MLP_PARAMS + 31) / 32, 256, 0, st>>>(workspace, grid, grad_mlp, 0);
     MF_LAUNCH_CHECK();
     return MF_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Active-point compaction.  A point whose upstream gradient row d_raw[i][0..9] is all zero (a sample behind the
+// surface: no loss term sees it, helper_functions/utils.py:21-47) adds exactly zero to every gradient, so the
+// backward kernels skip it.  Ordered (ascending point index => run-to-run deterministic tiles), two small kernels:
+// flags + per-block counts, then every block sums the counts before it and writes its ranks.
+// ---------------------------------------------------------------------------------------------
+constexpr int ACT_BLK = 1024;
+
+__global__ void __launch_bounds__(ACT_BLK) active_count_kernel(const float* __restrict__ d_raw, int64_t N,
+                                                               uint32_t* __restrict__ flags, int* __restrict__ blk_cnt) {
+    const int64_t i = (int64_t)blockIdx.x * ACT_BLK + threadIdx.x;
+    bool on = false;
+    if (i < N) {
+        const float2* g = reinterpret_cast<const float2*>(d_raw + i * MF_RAW_DIM);      // 40-byte rows: 8-byte aligned
+#pragma unroll
+        for (int k = 0; k < MF_RAW_DIM / 2; ++k) { const float2 v = __ldg(g + k); on |= (v.x != 0.f) | (v.y != 0.f); }
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31) == 0) flags[i >> 5] = word;
+    const int total = __syncthreads_count(on);
+    if (threadIdx.x == 0) blk_cnt[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(ACT_BLK) active_fill_kernel(const uint32_t* __restrict__ flags, const int* __restrict__ blk_cnt,
+                                                              int* __restrict__ idx, int* __restrict__ n_active) {
+    __shared__ int wsum[32];
+    __shared__ int base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int part = 0;
+    for (int j = tid; j < (int)blockIdx.x; j += ACT_BLK) part += blk_cnt[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) wsum[warp] = part;
+    __syncthreads();
+    if (warp == 0) {
+        int v = wsum[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) base_s = v;
+    }
+    __syncthreads();
+    const int base = base_s;
+    const int64_t i = (int64_t)blockIdx.x * ACT_BLK + tid;
+    const uint32_t word = flags[i >> 5];                      // the flag array is padded to whole blocks
+    __syncthreads();
+    if (lane == 0) wsum[warp] = __popc(word);
+    __syncthreads();
+    if (warp == 0) {                                          // exclusive scan of the 32 warp counts
+        const int c = wsum[lane];
+        int v = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+        wsum[lane] = v - c;
+        if (lane == 31 && blockIdx.x == gridDim.x - 1) *n_active = base + v;
+    }
+    __syncthreads();
+    if ((word >> lane) & 1u) idx[base + wsum[warp] + __popc(word & ((1u << lane) - 1u))] = (int)i;
+}
+
+static inline int64_t act_blocks(int64_t N) { return (N + ACT_BLK - 1) / ACT_BLK; }
+// scratch (in 4-byte words) behind the partials / point gradients: idx[N] | flags[blocks * 32] | blk_cnt[blocks] | count
+static inline int64_t act_scratch_words(int64_t N) { return N + act_blocks(N) * 33 + 4; }
+
+static int compact_active_points(const float* d_raw, int64_t N, float* scratch, ActiveMap* am, cudaStream_t st) {
+    if (N >= (int64_t)1 << 31) { mf_set_error("backward: more than 2^31 points"); return MF_ERR_INVALID; }
+    const int64_t nb = act_blocks(N);
+    int* idx = reinterpret_cast<int*>(scratch);
+    uint32_t* flags = reinterpret_cast<uint32_t*>(idx + N);
+    int* blk_cnt = reinterpret_cast<int*>(flags + nb * 32);
+    int* count = blk_cnt + nb;
+    active_count_kernel<<<(unsigned)nb, ACT_BLK, 0, st>>>(d_raw, N, flags, blk_cnt);
+    MF_LAUNCH_CHECK();
+    active_fill_kernel<<<(unsigned)nb, ACT_BLK, 0, st>>>(flags, blk_cnt, idx, count);
+    MF_LAUNCH_CHECK();
+    am->idx = idx; am->count = count;
+    return MF_OK;
+}
+
+MF_API int64_t mf_field_bwd_workspace_size(int64_t n_points, int want_point_grads) {
+    if (n_points < 0) n_points = 0;
+    return mf_mlp_grad_workspace_size() + (want_point_grads ? 3 * n_points : 0) + act_scratch_words(n_points);
+}
+
 template <class Src>
 static int launch_field_bwd(const FieldDev& d, const Src& src, const float* d_raw, float* grad_grid, float* grad_mlp,
-                            float* d_pts, float* workspace, int64_t N, cudaStream_t st) {
+                            float* d_pts, float* workspace, float* scratch, int64_t N, cudaStream_t st) {
+    // workspace: per-CTA partials; scratch: act_scratch_words(N) words for the active-point list
+    ActiveMap am{nullptr, nullptr};
+    int rc0 = compact_active_points(d_raw, N, scratch, &am, st); if (rc0) return rc0;
+    if (d_pts) MF_CUDA(cudaMemsetAsync(d_pts, 0, (size_t)N * 3 * sizeof(float), st));   // skipped points: exactly zero
     if (d.impl != 1) {                                 // tcgen05 path: 128-point tiles, one CTA per SM
         const int64_t tiles = (N + TC_TP - 1) / TC_TP;
         const int64_t cap = mf_sm_count_cached();
         const int grid = (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
         if (d_pts) {
             int rc = set_smem(field_bwd_tc_kernel<Src, true>, SMEM_TC_BWD); if (rc) return rc;
-            field_bwd_tc_kernel<Src, true><<<grid, TC_NT, SMEM_TC_BWD, st>>>(d, src, d_raw, grad_grid, workspace, d_pts, N, mf_tc_error_flag(), mf_tc_profile_buffer());
+            field_bwd_tc_kernel<Src, true><<<grid, TC_NT, SMEM_TC_BWD, st>>>(d, src, d_raw, grad_grid, workspace, d_pts, N, am, mf_tc_error_flag(), mf_tc_profile_buffer());
         } else {
             int rc = set_smem(field_bwd_tc_kernel<Src, false>, SMEM_TC_BWD); if (rc) return rc;
-            field_bwd_tc_kernel<Src, false><<<grid, TC_NT, SMEM_TC_BWD, st>>>(d, src, d_raw, grad_grid, workspace, nullptr, N, mf_tc_error_flag(), mf_tc_profile_buffer());
+            field_bwd_tc_kernel<Src, false><<<grid, TC_NT, SMEM_TC_BWD, st>>>(d, src, d_raw, grad_grid, workspace, nullptr, N, am, mf_tc_error_flag(), mf_tc_profile_buffer());
         }
         MF_LAUNCH_CHECK();
-        reduce_partials_kernel<<<(MF_MLP_PARAMS + 255) / 256, 256, 0, st>>>(workspace, grid, grad_mlp, 1);
+        reduce_partials_kernel<<<(MF_MLP_PARAMS + 31) / 32, 256, 0, st>>>(workspace, grid, grad_mlp, 1);
         MF_LAUNCH_CHECK();
         return MF_OK;
     }
     const int grid = persistent_grid(N, 1);
     if (d_pts) {
         int rc = set_smem(field_bwd_kernel<Src, true>, SMEM_BWD); if (rc) return rc;
-        field_bwd_kernel<Src, true><<<grid, NT, SMEM_BWD, st>>>(d, src, d_raw, grad_grid, workspace, d_pts, N);
+        field_bwd_kernel<Src, true><<<grid, NT, SMEM_BWD, st>>>(d, src, d_raw, grad_grid, workspace, d_pts, N, am);
     } else {
         int rc = set_smem(field_bwd_kernel<Src, false>, SMEM_BWD); if (rc) return rc;
-        field_bwd_kernel<Src, false><<<grid, NT, SMEM_BWD, st>>>(d, src, d_raw, grad_grid, workspace, nullptr, N);
+        field_bwd_kernel<Src, false><<<grid, NT, SMEM_BWD, st>>>(d, src, d_raw, grad_grid, workspace, nullptr, N, am);
     }
     MF_LAUNCH_CHECK();
-    reduce_partials_kernel<<<(MF_MLP_PARAMS + 255) / 256, 256, 0, st>>>(workspace, grid, grad_mlp, 0);
+    reduce_partials_kernel<<<(MF_MLP_PARAMS + 31) / 32, 256, 0, st>>>(workspace, grid, grad_mlp, 0);
     MF_LAUNCH_CHECK();
     return MF_OK;
 }
@@ -462,9 +567,11 @@ MF_API int mf_field_query_bwd(const float* pts, const mf_field* field, int norma
     MF_CHECK_ARG(N >= 0);
     if (N == 0) return MF_OK;
     MF_CHECK_ARG(pts && d_out && grad_grid && grad_mlp && workspace);
+    MF_CHECK_ARG(((uintptr_t)grad_grid & 15) == 0);          // the scatter uses 16-byte reductions
     FieldDev d; int rc = mf_field_to_dev(field, &d); if (rc) return rc;
     SrcPoints src{pts, normalize};
-    return launch_field_bwd(d, src, d_out, grad_grid, grad_mlp, d_pts, workspace, N, (cudaStream_t)stream);
+    return launch_field_bwd(d, src, d_out, grad_grid, grad_mlp, d_pts, workspace, workspace + mf_mlp_grad_workspace_size(), N,
+                            (cudaStream_t)stream);
 }
 
 MF_API int64_t mf_feat_cache_size(int64_t n_points) {
@@ -488,6 +595,7 @@ MF_API int mf_field_query_rays_bwd(const float* rays_o, const float* rays_d, con
     MF_CHECK_ARG(R >= 0 && S > 0);
     if (R == 0) return MF_OK;
     MF_CHECK_ARG(rays_o && rays_d && z && d_raw && grad_grid && grad_mlp && workspace);
+    MF_CHECK_ARG(((uintptr_t)grad_grid & 15) == 0);          // the scatter uses 16-byte reductions
     MF_CHECK_ARG((d_rays_o == nullptr) == (d_rays_d == nullptr));
     FieldDev d; int rc = mf_field_to_dev(field, &d); if (rc) return rc;
     d.feat = (uint32_t*)feat;
@@ -495,7 +603,8 @@ MF_API int mf_field_query_rays_bwd(const float* rays_o, const float* rays_d, con
     cudaStream_t st = (cudaStream_t)stream;
     // the per-point dL/dp buffer lives behind the per-CTA partials in the workspace
     float* d_pts = d_rays_o ? workspace + mf_mlp_grad_workspace_size() : nullptr;
-    rc = launch_field_bwd(d, src, d_raw, grad_grid, grad_mlp, d_pts, workspace, R * S, st);
+    float* scratch = workspace + mf_mlp_grad_workspace_size() + (d_rays_o ? 3 * R * S : 0);
+    rc = launch_field_bwd(d, src, d_raw, grad_grid, grad_mlp, d_pts, workspace, scratch, R * S, st);
     if (rc) return rc;
     if (d_rays_o) {
         ray_grad_reduce_kernel<<<(unsigned)((R + 7) / 8), 256, 0, st>>>(d_pts, z, d_rays_o, d_rays_d, R, S);

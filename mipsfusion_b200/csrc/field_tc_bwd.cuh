@@ -234,8 +234,8 @@ __device__ __forceinline__ void tb_wgrad_layer(TbCtx& c, int p, int q, const flo
 template <class Src, bool WANT_DX>
 __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src src, const float* __restrict__ d_raw,
                                                                 float* __restrict__ grad_grid, float* __restrict__ part,
-                                                                float* __restrict__ d_pts, int64_t N, int* __restrict__ err,
-                                                                long long* __restrict__ prof) {
+                                                                float* __restrict__ d_pts, int64_t N_all, ActiveMap am,
+                                                                int* __restrict__ err, long long* __restrict__ prof) {
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x, p = tid & (TC_TP - 1), q = tid >> 7, lane = tid & 31;
 #define TB_MARK(k) do { if (prof && tid == 0 && blockIdx.x == 0 && tile == (int64_t)gridDim.x) prof[k] = clock64(); } while (0)
@@ -245,10 +245,12 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
     tb_setup(c, smem_raw, f.tc_img);
     const float2* grid2 = reinterpret_cast<const float2*>(f.grid);
 
+    const int64_t N = am.n(N_all);                     // active points only (ascending point indices in am.idx)
     const int64_t n_tiles = (N + TC_TP - 1) / TC_TP;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t i = tile * TC_TP + p;
-        const bool valid = i < N;
+        const int64_t slot = tile * TC_TP + p;
+        const bool valid = slot < N;
+        const int64_t i = valid ? am(slot) : 0;
         TB_MARK(0);
         // ---- W1 image into region 1 (it doubles as the wgrad dZ tile later in the tile) ----
         tb_copy(c.r1, f.tc_img + IMG_W1_HI, 2 * IMG_BLOCK);
@@ -259,7 +261,8 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
         // ---- encode (or reload the operand words the forward kernel cached) ----
         float x[3] = {0.f, 0.f, 0.f};
         if (valid) src.point(i, f, x);
-        const uint32_t* fin = f.feat ? f.feat + (size_t)tile * FEAT_TILE_WORDS + (size_t)q * FEAT_WORDS * TC_TP + p : nullptr;
+        // the forward cached the operand words of point i at [i / 128][q][word][i % 128]
+        const uint32_t* fin = f.feat ? f.feat + (size_t)(i >> 7) * FEAT_TILE_WORDS + (size_t)q * FEAT_WORDS * TC_TP + (i & (TC_TP - 1)) : nullptr;
         {
             float e[16];
             uint32_t hi[8], lo[8];

@@ -91,6 +91,10 @@ __device__ __forceinline__ void red_add_f2(float* addr, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
+__device__ __forceinline__ void red_add_f4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // Backward of one level: scatter w * dy into grad (kernel_grid_backward) and, if WANT_DX,
 // return dL/dx contribution (kernel_grid_backward_input; needs the forward features).
 template <bool WANT_DX>
@@ -99,8 +103,21 @@ __device__ __forceinline__ void grid_level_bwd(const float x[3], float2 dy, cons
     uint32_t idx[8]; float w8[8];
     grid_corners(x, li, idx, w8);
     if (dy.x != 0.f || dy.y != 0.f) {
+        // the two corners of an x-pair are neighbours in the table whenever their indices differ only in bit 0 (cell x even
+        // on a hashed level, even linear index on a dense one; level offsets are multiples of 8): one 16-byte reduction
+        // instead of two 8-byte ones -- the scatter is bound by reduction lanes per SM
 #pragma unroll
-        for (int c = 0; c < 8; ++c) red_add_f2(grad + 2 * (size_t)(li.offset + idx[c]), w8[c] * dy.x, w8[c] * dy.y);
+        for (int c = 0; c < 8; c += 2) {
+            const uint32_t i0 = idx[c], i1 = idx[c + 1];
+            if ((i0 ^ i1) == 1u) {
+                const bool sw = (i0 & 1u) != 0u;                       // i1 is the even (lower) entry
+                const float wa = sw ? w8[c + 1] : w8[c], wb = sw ? w8[c] : w8[c + 1];
+                red_add_f4(grad + 2 * (size_t)(li.offset + (i0 & ~1u)), wa * dy.x, wa * dy.y, wb * dy.x, wb * dy.y);
+            } else {
+                red_add_f2(grad + 2 * (size_t)(li.offset + i0), w8[c] * dy.x, w8[c] * dy.y);
+                red_add_f2(grad + 2 * (size_t)(li.offset + i1), w8[c + 1] * dy.x, w8[c + 1] * dy.y);
+            }
+        }
     }
     if (WANT_DX) {
         float f[3];

@@ -93,6 +93,15 @@ struct FieldDev {
     uint32_t res[MF_MAX_LEVELS], size[MF_MAX_LEVELS], offset[MF_MAX_LEVELS], hashed[MF_MAX_LEVELS];
 };
 
+// Backward kernels only visit the points whose upstream gradient row is non-zero ("active" points; the others add
+// exactly zero to every gradient).  idx (ascending point indices) and count live in the caller's workspace and are
+// written by compact_active_points(); idx == nullptr is the identity map over [0, N).
+struct ActiveMap {
+    const int* idx; const int* count;
+    __device__ __forceinline__ int64_t n(int64_t N) const { return count ? (int64_t)*count : N; }
+    __device__ __forceinline__ int64_t operator()(int64_t slot) const { return idx ? (int64_t)idx[slot] : slot; }
+};
+
 int mf_field_to_dev(const mf_field* f, FieldDev* d);   // validates (16 levels, 2 features)
 int mf_decoder_impl();                                 // 0: tcgen05 tensor cores (default), 1: fp32 CUDA cores
 int* mf_tc_error_flag();

@@ -16,8 +16,13 @@ class _Workspace:
     _bufs = {}
 
     @classmethod
-    def get(cls, device, extra_floats=0):
-        n = int(L.lib().mf_mlp_grad_workspace_size()) + int(extra_floats)
+    def get(cls, device, extra_floats=0, field_points=None, want_ray_grads=False):
+        """field_points: size the buffer for a fused field backward over that many points
+        (mf_field_bwd_workspace_size), otherwise for the stand-alone decoder backward."""
+        if field_points is not None:
+            n = int(L.lib().mf_field_bwd_workspace_size(int(field_points), int(bool(want_ray_grads))))
+        else:
+            n = int(L.lib().mf_mlp_grad_workspace_size()) + int(extra_floats)
         key = (device.type, device.index)
         buf = cls._bufs.get(key)
         if buf is None or buf.numel() < n:

@@ -96,7 +96,7 @@ class FusedMapper:
                L.ptr(b["losses"]), C.byref(cfg), L.ptr(self.loss_w), None, None, L.ptr(b["d_raw"]), R, S, st)
         e3 = ev()
         L.call("mf_field_query_rays_bwd", L.ptr(rays_o), L.ptr(rays_d), L.ptr(b["z"]), C.byref(field), L.ptr(b["d_raw"]),
-               L.ptr(b["feat"]), L.ptr(self.g_grid), L.ptr(self.g_mlp), None, None, L.ptr(_Workspace.get(self.dev)), R, S, st)
+               L.ptr(b["feat"]), L.ptr(self.g_grid), L.ptr(self.g_mlp), None, None, L.ptr(_Workspace.get(self.dev, field_points=R * S)), R, S, st)
         e4 = ev()
         self.launches += 7
         if update:

@@ -53,7 +53,7 @@ class _FieldQueryFn(torch.autograd.Function):
         g_mlp = torch.zeros(L.MF_MLP_PARAMS, device=pts.device, dtype=torch.float32)
         d_pts = torch.empty_like(pts) if ctx.needs_input_grad[0] else None
         d_out = d_out.contiguous()                     # bound to a name: a temporary could be recycled before the launch
-        ws = _Workspace.get(pts.device)
+        ws = _Workspace.get(pts.device, field_points=N)
         L.call("mf_field_query_bwd", L.ptr(pts), C.byref(field), int(ctx.normalize), L.ptr(d_out), L.ptr(g_grid),
                L.ptr(g_mlp), L.ptr(d_pts), L.ptr(ws), N, L.stream())
         return (d_pts, None, None, g_grid, *_split(g_mlp, ctx.shapes))
@@ -129,7 +129,7 @@ class _RenderFn(torch.autograd.Function):
         g_mlp = torch.zeros(L.MF_MLP_PARAMS, device=dev, dtype=torch.float32)
         d_o = torch.empty_like(rays_o) if want_rays else None
         d_d = torch.empty_like(rays_d) if want_rays else None
-        ws = _Workspace.get(dev, 3 * R * S if want_rays else 0)
+        ws = _Workspace.get(dev, field_points=R * S, want_ray_grads=want_rays)
         L.call("mf_field_query_rays_bwd", L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), C.byref(field), L.ptr(d_raw), L.ptr(ctx.feat),
                L.ptr(g_grid), L.ptr(g_mlp), L.ptr(d_o), L.ptr(d_d), L.ptr(ws), R, S, st)
         return (d_o, d_d, None, None, None, None, None, g_grid, *_split(g_mlp, ctx.shapes))

@@ -25,7 +25,7 @@ def test_library_loads_and_exports_every_symbol():
     dll = L.load_library()
     for name in header_functions():
         assert hasattr(dll, name), name
-    assert dll.mf_abi_version() == 1
+    assert dll.mf_abi_version() == 2
     assert dll.mf_mlp_prep_size() > L.MF_MLP_PARAMS
 
 
