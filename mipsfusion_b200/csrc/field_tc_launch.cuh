@@ -3,6 +3,7 @@
 #include "field_launch.cuh"
 #include "field_tc.cuh"
 #include "field_tc2.cuh"
+#include "field_tc3.cuh"
 
 template <class Src, class Epi, bool SDF_ONLY>
 static inline int launch_field_fwd_tc(const FieldDev& d, const Src& src, const Epi& epi, int64_t N, cudaStream_t st,
@@ -29,10 +30,27 @@ static inline int launch_field_fwd_tc2(const FieldDev& d, const Src& src, const 
     return MF_OK;
 }
 
+// producer / consumer kernel: gather warps feed decoder warps through tensor memory
+template <class Src, class Epi, bool SDF_ONLY>
+static inline int launch_field_fwd_tc3(const FieldDev& d, const Src& src, const Epi& epi, int64_t N, cudaStream_t st,
+                                       const unsigned int* n_dev = nullptr) {
+    int rc = set_smem(field_fwd_tc3_kernel<Src, Epi, SDF_ONLY>, SMEM_TC3); if (rc) return rc;
+    const int64_t tiles = (N + TC_TP - 1) / TC_TP;
+    const int64_t cap = mf_sm_count_cached();
+    const int grid = (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
+    field_fwd_tc3_kernel<Src, Epi, SDF_ONLY><<<grid, 2 * T3_GT, SMEM_TC3, st>>>(d, src, epi, N, n_dev, d.tc_img, mf_tc_error_flag(), mf_tc_profile_buffer());
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}
+
 template <class Src, class Epi, bool SDF_ONLY>
 static inline int launch_field_fwd_auto(const FieldDev& d, const Src& src, const Epi& epi, int64_t N, cudaStream_t st,
-                                        const unsigned int* n_dev = nullptr) {
-    if (d.impl == 0) return launch_field_fwd_tc2<Src, Epi, SDF_ONLY>(d, src, epi, N, st, n_dev);
+                                        const unsigned int* n_dev = nullptr, bool short_launches = false) {
+    // short launches (a few tiles per CTA, e.g. the per-submap chunks of the joint query) cannot fill the
+    // producer -> consumer pipeline; two independent tiles per CTA (dual pipeline) serve them better
+    if (d.impl == 0 && short_launches) return launch_field_fwd_tc2<Src, Epi, SDF_ONLY>(d, src, epi, N, st, n_dev);
+    if (d.impl == 0) return launch_field_fwd_tc3<Src, Epi, SDF_ONLY>(d, src, epi, N, st, n_dev);
+    if (d.impl == 3) return launch_field_fwd_tc2<Src, Epi, SDF_ONLY>(d, src, epi, N, st, n_dev);   // dual pipeline (A/B)
     if (d.impl == 2) return launch_field_fwd_tc<Src, Epi, SDF_ONLY>(d, src, epi, N, st, n_dev);   // single pipeline (A/B)
     return launch_field_fwd<Src, Epi, SDF_ONLY>(d, src, epi, N, st, n_dev);
 }

@@ -180,8 +180,8 @@ MF_API int mf_joint_query_accumulate(const mf_point_set* ps, const mf_submap* su
             MF_LAUNCH_CHECK();
             SrcJoint src{p, sub, list, g_begin + c_begin};
             EpiJoint epi{p, sub, list, g_begin + c_begin, c_begin, vis, M, m, max_dist, color, acc, mask_any};
-            if (color) rc = launch_field_fwd_auto<SrcJoint, EpiJoint, false>(d, src, epi, c_count, st, counter);
-            else rc = launch_field_fwd_auto<SrcJoint, EpiJoint, true>(d, src, epi, c_count, st, counter);
+            if (color) rc = launch_field_fwd_auto<SrcJoint, EpiJoint, false>(d, src, epi, c_count, st, counter, true);
+            else rc = launch_field_fwd_auto<SrcJoint, EpiJoint, true>(d, src, epi, c_count, st, counter, true);
             if (rc) return rc;
         }
     }

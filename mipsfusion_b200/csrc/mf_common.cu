@@ -39,7 +39,9 @@ static int g_decoder_impl = 0;
 int mf_decoder_impl() { return g_decoder_impl; }
 
 MF_API int mf_set_decoder_impl(int impl) {
-    MF_CHECK_ARG(impl == 0 || impl == 1 || impl == 2);   // 2: single-pipeline tcgen05 forward (A/B comparisons)
+    // 0: tcgen05 (producer / consumer forward), 1: fp32 CUDA cores; A/B comparisons of the tcgen05 forward:
+    // 2: single pipeline, 3: dual pipeline
+    MF_CHECK_ARG(impl >= 0 && impl <= 3);
     g_decoder_impl = impl;
     return MF_OK;
 }
