@@ -163,6 +163,8 @@ def run_gpu(args):
     group = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"           # keep NCCL's version banner off the JSON stream
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     cfg, of = build_model()

@@ -78,6 +78,72 @@ MF_API int mf_adam_step(float* p, float* g, float* m, float* v, int64_t n, doubl
     return MF_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Data-parallel mapping: gradient reduce-scatter + Adam + parameter all-gather in ONE kernel over NVLink peer memory.
+// Every rank holds the same arena layout in symmetric (peer-mapped) memory; rank r owns the r-th slab of the
+// parameters: it reads that slab of the gradient from every rank (fixed rank order -> all replicas receive bit-identical
+// parameters), averages, applies Adam with its slab of the moments and stores the new parameters into every rank's
+// copy.  Per GPU the links carry 2 (W-1)/W of the parameter bytes instead of a full all-reduce followed by a replicated
+// Adam pass, and the moments are only touched on the owning rank.  The caller brackets the launch with cross-GPU barriers.
+// ---------------------------------------------------------------------------------------------
+constexpr int MF_MAX_PEERS = 16;
+struct PeerPtrs { float* p[MF_MAX_PEERS]; const float* g[MF_MAX_PEERS]; };
+
+__global__ void __launch_bounds__(256) adam_sharded_kernel(PeerPtrs peers, int world, float inv_world, float4* __restrict__ m,
+                                                           float4* __restrict__ v, float4* __restrict__ g_clear, int64_t begin4,
+                                                           int64_t end4, int64_t n4, AdamScalars a) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = begin4 + t0; i < end4; i += stride) {
+        float4 gg = reinterpret_cast<const float4*>(peers.g[0])[i];
+        for (int r = 1; r < world; ++r) {
+            const float4 o = reinterpret_cast<const float4*>(peers.g[r])[i];
+            gg.x += o.x; gg.y += o.y; gg.z += o.z; gg.w += o.w;
+        }
+        gg.x *= inv_world; gg.y *= inv_world; gg.z *= inv_world; gg.w *= inv_world;
+        float4 pp = reinterpret_cast<const float4*>(peers.p[0])[i];      // all replicas hold the same parameters
+        float4 mm = m[i], vv = v[i];
+        adam_one(pp.x, gg.x, mm.x, vv.x, a); adam_one(pp.y, gg.y, mm.y, vv.y, a);
+        adam_one(pp.z, gg.z, mm.z, vv.z, a); adam_one(pp.w, gg.w, mm.w, vv.w, a);
+        m[i] = mm; v[i] = vv;
+        for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(peers.p[r])[i] = pp;
+    }
+    if (g_clear)                                                         // zero_grad of the buffer the NEXT backward accumulates into
+        for (int64_t i = t0; i < n4; i += stride) g_clear[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+MF_API int mf_adam_step_sharded(const uint64_t* peer_bases, int world, int rank, int64_t off_p, int64_t off_g, int64_t off_g_clear,
+                                float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
+                                double weight_decay, int step, void* stream) {
+    MF_CHECK_ARG(peer_bases && world >= 1 && world <= MF_MAX_PEERS && rank >= 0 && rank < world);
+    MF_CHECK_ARG(n >= 0 && (n & 3) == 0 && step >= 1 && m && v);
+    MF_CHECK_ARG(((off_p | off_g) & 3) == 0 && (off_g_clear < 0 || (off_g_clear & 3) == 0));
+    if (n == 0) return MF_OK;
+    PeerPtrs peers;
+    for (int r = 0; r < world; ++r) {
+        MF_CHECK_ARG(peer_bases[r] && (peer_bases[r] & 15) == 0);
+        peers.p[r] = reinterpret_cast<float*>(peer_bases[r]) + off_p;
+        peers.g[r] = reinterpret_cast<const float*>(peer_bases[r]) + off_g;
+    }
+    // the kernel reads the parameters through slot 0 and writes through every slot: put the local copy in slot 0
+    { float* t = peers.p[0]; peers.p[0] = peers.p[rank]; peers.p[rank] = t; }
+    MF_CHECK_ARG((((uintptr_t)m | (uintptr_t)v) & 15) == 0);
+    AdamScalars a;
+    a.w1 = (float)(1.0 - beta1); a.beta2 = (float)beta2; a.w2 = (float)(1.0 - beta2);
+    a.neg_step = (float)(-(lr / (1.0 - pow(beta1, (double)step))));
+    a.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
+    a.eps = (float)eps; a.wd = (float)weight_decay;
+    const int64_t n4 = n / 4, per = (n4 + world - 1) / world;
+    const int64_t begin4 = per * rank < n4 ? per * rank : n4, end4 = begin4 + per < n4 ? begin4 + per : n4;
+    float4* clear = off_g_clear >= 0 ? reinterpret_cast<float4*>(reinterpret_cast<float*>(peer_bases[rank]) + off_g_clear) : nullptr;
+    const int64_t work = clear ? n4 : (end4 - begin4);
+    const int64_t want = (work + 255) / 256, cap = (int64_t)mf_sm_count_cached() * 8;
+    const unsigned blocks = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+    adam_sharded_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(peers, world, (float)(1.0 / world), (float4*)m, (float4*)v, clear,
+                                                                  begin4, end4, n4, a);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}
+
 MF_API int mf_adam_step_multi(int n_tensors, float* const* p, float* const* g, float* const* m, float* const* v,
                               const int64_t* n, double lr, double beta1, double beta2, double eps, double weight_decay,
                               int step, int zero_grad, void* stream) {

@@ -61,3 +61,35 @@ def average_gradients_(tensors, group):
         allreduce_sum_(t, group)
         t.mul_(1.0 / ws)
     return tensors
+
+
+class PeerArena:
+    """One float32 arena per rank in symmetric (peer-mapped) memory: every rank can load / store every other rank's
+    copy over NVLink with plain pointers.  Used by the data-parallel mapper to fuse the gradient reduce-scatter, Adam
+    and the parameter all-gather into one kernel (mf_adam_step_sharded).  ``regions``: dict name -> number of floats
+    (each region is padded to a multiple of 4 floats, 16-byte aligned)."""
+
+    def __init__(self, regions, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.offsets, self.sizes = {}, {}
+        off = 0
+        for name, n in regions.items():
+            n4 = (int(n) + 3) // 4 * 4
+            self.offsets[name], self.sizes[name] = off, n4
+            off += n4
+        self.group = group
+        self.world, self.rank = world(group)
+        self.buf = symm_mem.empty(off, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group.group_name if hasattr(group, "group_name") else group)
+        self.peer_bases = [int(x) for x in self.handle.buffer_ptrs]
+        if len(self.peer_bases) != self.world:
+            raise RuntimeError("symmetric memory rendezvous returned %d peers for a world of %d" % (len(self.peer_bases), self.world))
+
+    def view(self, name, n=None):
+        o = self.offsets[name]
+        return self.buf[o:o + (self.sizes[name] if n is None else int(n))]
+
+    def barrier(self):
+        """Cross-GPU barrier on the current stream (device side, no host synchronisation)."""
+        self.handle.barrier(channel=0)

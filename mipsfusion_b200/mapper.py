@@ -17,7 +17,7 @@ from .decoder import _Workspace
 
 
 class FusedMapper:
-    def __init__(self, model, lr_decoder=None, lr_embed=None, group=None):
+    def __init__(self, model, lr_decoder=None, lr_embed=None, group=None, peer_memory="auto"):
         self.model = model
         cfg = model.config
         self.dev = model._device
@@ -36,12 +36,42 @@ class FusedMapper:
         self.prep = torch.empty(int(L.lib().mf_mlp_prep_size()), device=self.dev, dtype=torch.float32)
         self.g_grid = torch.zeros_like(self.grid); self.m_grid = torch.zeros_like(self.grid); self.v_grid = torch.zeros_like(self.grid)
         self.g_mlp = torch.zeros_like(self.mlp); self.m_mlp = torch.zeros_like(self.mlp); self.v_mlp = torch.zeros_like(self.mlp)
+        # Data parallel with NVLink peer memory: parameters and (double-buffered) gradients live in a symmetric arena and
+        # the gradient all-reduce + Adam + parameter broadcast become one sharded kernel (mf_adam_step_sharded).
+        # peer_memory: True (require), False (NCCL all-reduce + replicated Adam), "auto" (try, fall back to NCCL).
+        self.arena = None
+        if self.world > 1 and peer_memory:
+            try:
+                self._init_peer_arena()
+            except Exception as e:                                   # no P2P / symmetric memory on this box
+                if peer_memory is True:
+                    raise
+                import warnings
+                warnings.warn("FusedMapper: peer memory unavailable (%s); using NCCL all-reduce" % (e,))
+                self.arena = None
         self.step_count = 0
         self._bufs = {}
         self.timing = None            # optional dict name -> (start_event, end_event) lists
         self.launches = 0
         with torch.cuda.device(self.dev):
             L.call("mf_mlp_prepare", L.ptr(self.mlp), L.ptr(self.prep), L.stream())
+
+    def _init_peer_arena(self):
+        ng, nm = self.grid.numel(), self.mlp.numel()
+        arena = D.PeerArena({"p_grid": ng, "g_grid0": ng, "g_grid1": ng, "p_mlp": nm, "g_mlp0": nm, "g_mlp1": nm}, self.dev, self.group)
+        arena.view("p_grid", ng).copy_(self.grid)
+        arena.view("p_mlp", nm).copy_(self.mlp)
+        self.grid = arena.view("p_grid", ng)
+        self.model.embed_fn.params.data = self.grid                 # the module now reads the arena copy
+        self.mlp = arena.view("p_mlp", nm)
+        self._g_grid = [arena.view("g_grid0", ng), arena.view("g_grid1", ng)]
+        self._g_mlp = [arena.view("g_mlp0", nm), arena.view("g_mlp1", nm)]
+        self.g_grid, self.g_mlp = self._g_grid[0], self._g_mlp[0]
+        nm4 = arena.sizes["p_mlp"]
+        self.m_mlp = torch.zeros(nm4, device=self.dev); self.v_mlp = torch.zeros(nm4, device=self.dev)
+        self.arena = arena
+        torch.cuda.current_stream(self.dev).synchronize()
+        arena.barrier()
 
     def _buffers(self, R, S):
         key = (R, S)
@@ -100,8 +130,11 @@ class FusedMapper:
         e4 = ev()
         self.launches += 7
         if update:
-            D.average_gradients_([self.g_grid, self.g_mlp], self.group)
-            self.apply_gradients()
+            if self.arena is not None:
+                self.apply_gradients_sharded()
+            else:
+                D.average_gradients_([self.g_grid, self.g_mlp], self.group)
+                self.apply_gradients()
         e5 = ev()
         if tm is not None:
             for name, a, c in (("sample_z", e0, e1), ("field_fwd", e1, e2), ("render_loss", e2, e3), ("field_bwd", e3, e4),
@@ -143,6 +176,25 @@ class FusedMapper:
                float(self.lr_embed), 0.9, 0.99, 1e-15, 0.0, self.step_count, 1, st)
         L.call("mf_adam_step", L.ptr(self.mlp), L.ptr(self.g_mlp), L.ptr(self.m_mlp), L.ptr(self.v_mlp), self.mlp.numel(),
                float(self.lr_decoder), 0.9, 0.99, 1e-8, 1e-6, self.step_count, 1, st)
+        L.call("mf_mlp_prepare", L.ptr(self.mlp), L.ptr(self.prep), st)
+        self.launches += 4
+
+    def apply_gradients_sharded(self):
+        """Data-parallel update over peer memory: barrier, one sharded reduce + Adam + broadcast kernel per tensor,
+        barrier.  The gradient buffers alternate between steps; the kernel clears the one the next backward uses."""
+        self.step_count += 1
+        a, st = self.arena, L.stream()
+        cur, nxt = (self.step_count - 1) & 1, self.step_count & 1
+        bases = (C.c_uint64 * a.world)(*a.peer_bases)
+        a.barrier()                                                  # every rank's gradients are complete
+        L.call("mf_adam_step_sharded", bases, a.world, a.rank, a.offsets["p_grid"], a.offsets["g_grid%d" % cur],
+               a.offsets["g_grid%d" % nxt], L.ptr(self.m_grid), L.ptr(self.v_grid), a.sizes["p_grid"],
+               float(self.lr_embed), 0.9, 0.99, 1e-15, 0.0, self.step_count, st)
+        L.call("mf_adam_step_sharded", bases, a.world, a.rank, a.offsets["p_mlp"], a.offsets["g_mlp%d" % cur],
+               a.offsets["g_mlp%d" % nxt], L.ptr(self.m_mlp), L.ptr(self.v_mlp), a.sizes["p_mlp"],
+               float(self.lr_decoder), 0.9, 0.99, 1e-8, 1e-6, self.step_count, st)
+        a.barrier()                                                  # every slab has reached every replica
+        self.g_grid, self.g_mlp = self._g_grid[nxt], self._g_mlp[nxt]
         L.call("mf_mlp_prepare", L.ptr(self.mlp), L.ptr(self.prep), st)
         self.launches += 4
 
