@@ -188,10 +188,12 @@ int mf_adam_step(float* p, float* g, float* m, float* v, int64_t n, double lr, d
  * offsets of the parameters, of the gradient to reduce and of the gradient buffer to zero (-1: none) inside the arena.
  * Rank r updates slab r of the n parameters (n % 4 == 0) with its local moments m, v (full-size arrays, only the slab
  * is touched) from the rank-ordered mean of all ranks' gradients and stores the result into every rank's parameters.
+ * multicast_base: address of the NVSwitch multicast mapping of the same arena (NVLS), or 0: with it the gradient sum is one
+ * multimem.ld_reduce (reduced in the switch) and the parameter broadcast one multimem.st.
  * The caller issues a cross-GPU barrier before (all gradients complete) and after (all slabs delivered) the call. */
 int mf_adam_step_sharded(const uint64_t* peer_bases, int world, int rank, int64_t off_p, int64_t off_g, int64_t off_g_clear,
                          float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
-                         double weight_decay, int step, void* stream);
+                         double weight_decay, int step, uint64_t multicast_base, void* stream);
 /* The same update for a parameter group of n_tensors tensors (host arrays of device pointers and sizes). */
 int mf_adam_step_multi(int n_tensors, float* const* p_host, float* const* g_host, float* const* m_host,
                        float* const* v_host, const int64_t* n_host, double lr, double beta1, double beta2, double eps,

@@ -89,23 +89,57 @@ MF_API int mf_adam_step(float* p, float* g, float* m, float* v, int64_t n, doubl
 constexpr int MF_MAX_PEERS = 16;
 struct PeerPtrs { float* p[MF_MAX_PEERS]; const float* g[MF_MAX_PEERS]; };
 
-__global__ void __launch_bounds__(256) adam_sharded_kernel(PeerPtrs peers, int world, float inv_world, float4* __restrict__ m,
+// W > 0: compile-time world size (all peer loads of an element are in flight together: the slab is small, so the kernel
+// is bound by NVLink latency unless every thread keeps W loads outstanding); W == 0: run-time world size.
+// MC: the arena also has an NVSwitch multicast mapping (NVLS): the gradient sum over all ranks is one
+// multimem.ld_reduce (reduced inside the switch) and the new parameters reach all replicas with one multimem.st, which
+// roughly halves the bytes each GPU's links carry.
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float4* mc) {
+    float4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+    return r;
+}
+__device__ __forceinline__ void multimem_st(float4* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int W, bool MC>
+__global__ void __launch_bounds__(256) adam_sharded_kernel(PeerPtrs peers, int world_rt, float inv_world, float4* __restrict__ m,
                                                            float4* __restrict__ v, float4* __restrict__ g_clear, int64_t begin4,
-                                                           int64_t end4, int64_t n4, AdamScalars a) {
+                                                           int64_t end4, int64_t n4, AdamScalars a, const float4* mc_g, float4* mc_p) {
+    const int world = W > 0 ? W : world_rt;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (int64_t i = begin4 + t0; i < end4; i += stride) {
-        float4 gg = reinterpret_cast<const float4*>(peers.g[0])[i];
-        for (int r = 1; r < world; ++r) {
-            const float4 o = reinterpret_cast<const float4*>(peers.g[r])[i];
-            gg.x += o.x; gg.y += o.y; gg.z += o.z; gg.w += o.w;
+        float4 gg;
+        if (MC) {
+            gg = multimem_ld_reduce_add(mc_g + i);
+        } else if (W > 0) {
+            float4 gs[W > 0 ? W : 1];
+#pragma unroll
+            for (int r = 0; r < W; ++r) gs[r] = reinterpret_cast<const float4*>(peers.g[r])[i];
+            gg = gs[0];
+#pragma unroll
+            for (int r = 1; r < W; ++r) { gg.x += gs[r].x; gg.y += gs[r].y; gg.z += gs[r].z; gg.w += gs[r].w; }
+        } else {
+            gg = reinterpret_cast<const float4*>(peers.g[0])[i];
+            for (int r = 1; r < world; ++r) {
+                const float4 o = reinterpret_cast<const float4*>(peers.g[r])[i];
+                gg.x += o.x; gg.y += o.y; gg.z += o.z; gg.w += o.w;
+            }
         }
         gg.x *= inv_world; gg.y *= inv_world; gg.z *= inv_world; gg.w *= inv_world;
-        float4 pp = reinterpret_cast<const float4*>(peers.p[0])[i];      // all replicas hold the same parameters
+        float4 pp = reinterpret_cast<const float4*>(peers.p[0])[i];      // slot 0 = the local copy; all replicas are identical
         float4 mm = m[i], vv = v[i];
         adam_one(pp.x, gg.x, mm.x, vv.x, a); adam_one(pp.y, gg.y, mm.y, vv.y, a);
         adam_one(pp.z, gg.z, mm.z, vv.z, a); adam_one(pp.w, gg.w, mm.w, vv.w, a);
         m[i] = mm; v[i] = vv;
-        for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(peers.p[r])[i] = pp;
+        if (MC) {
+            multimem_st(mc_p + i, pp);
+        } else {
+#pragma unroll
+            for (int r = 0; r < (W > 0 ? W : world); ++r) reinterpret_cast<float4*>(peers.p[r])[i] = pp;
+        }
     }
     if (g_clear)                                                         // zero_grad of the buffer the NEXT backward accumulates into
         for (int64_t i = t0; i < n4; i += stride) g_clear[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -113,7 +147,7 @@ __global__ void __launch_bounds__(256) adam_sharded_kernel(PeerPtrs peers, int w
 
 MF_API int mf_adam_step_sharded(const uint64_t* peer_bases, int world, int rank, int64_t off_p, int64_t off_g, int64_t off_g_clear,
                                 float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
-                                double weight_decay, int step, void* stream) {
+                                double weight_decay, int step, uint64_t multicast_base, void* stream) {
     MF_CHECK_ARG(peer_bases && world >= 1 && world <= MF_MAX_PEERS && rank >= 0 && rank < world);
     MF_CHECK_ARG(n >= 0 && (n & 3) == 0 && step >= 1 && m && v);
     MF_CHECK_ARG(((off_p | off_g) & 3) == 0 && (off_g_clear < 0 || (off_g_clear & 3) == 0));
@@ -138,8 +172,24 @@ MF_API int mf_adam_step_sharded(const uint64_t* peer_bases, int world, int rank,
     const int64_t work = clear ? n4 : (end4 - begin4);
     const int64_t want = (work + 255) / 256, cap = (int64_t)mf_sm_count_cached() * 8;
     const unsigned blocks = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
-    adam_sharded_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(peers, world, (float)(1.0 / world), (float4*)m, (float4*)v, clear,
-                                                                  begin4, end4, n4, a);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float inv = (float)(1.0 / world);
+    MF_CHECK_ARG((multicast_base & 15) == 0);
+    const float4* mc_g = multicast_base ? reinterpret_cast<const float4*>(reinterpret_cast<const float*>(multicast_base) + off_g) : nullptr;
+    float4* mc_p = multicast_base ? reinterpret_cast<float4*>(reinterpret_cast<float*>(multicast_base) + off_p) : nullptr;
+#define MF_LAUNCH_SHARDED(W, MC) adam_sharded_kernel<W, MC><<<blocks, 256, 0, st>>>(peers, world, inv, (float4*)m, (float4*)v, clear, \
+                                                                                    begin4, end4, n4, a, mc_g, mc_p)
+    if (multicast_base) {
+        MF_LAUNCH_SHARDED(0, true);
+    } else {
+        switch (world) {
+            case 2: MF_LAUNCH_SHARDED(2, false); break;
+            case 4: MF_LAUNCH_SHARDED(4, false); break;
+            case 8: MF_LAUNCH_SHARDED(8, false); break;
+            default: MF_LAUNCH_SHARDED(0, false); break;
+        }
+    }
+#undef MF_LAUNCH_SHARDED
     MF_LAUNCH_CHECK();
     return MF_OK;
 }

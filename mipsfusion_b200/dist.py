@@ -63,13 +63,18 @@ def average_gradients_(tensors, group):
     return tensors
 
 
+def DeviceTypeCUDA():
+    from torch._C._autograd import DeviceType
+    return DeviceType.CUDA
+
+
 class PeerArena:
     """One float32 arena per rank in symmetric (peer-mapped) memory: every rank can load / store every other rank's
     copy over NVLink with plain pointers.  Used by the data-parallel mapper to fuse the gradient reduce-scatter, Adam
     and the parameter all-gather into one kernel (mf_adam_step_sharded).  ``regions``: dict name -> number of floats
     (each region is padded to a multiple of 4 floats, 16-byte aligned)."""
 
-    def __init__(self, regions, device, group):
+    def __init__(self, regions, device, group, use_multicast=True):
         import torch.distributed._symmetric_memory as symm_mem
         self.offsets, self.sizes = {}, {}
         off = 0
@@ -83,6 +88,17 @@ class PeerArena:
         self.buf.zero_()
         self.handle = symm_mem.rendezvous(self.buf, group.group_name if hasattr(group, "group_name") else group)
         self.peer_bases = [int(x) for x in self.handle.buffer_ptrs]
+        # NVSwitch multicast mapping of the arena (NVLS), 0 when the fabric / driver does not offer it
+        self.multicast_base = 0
+        if use_multicast:
+            try:
+                if self.handle.has_multicast_support(DeviceTypeCUDA(), device.index if device.index is not None else torch.cuda.current_device()):
+                    self.multicast_base = int(self.handle.multicast_ptr or 0)
+            except Exception:
+                try:
+                    self.multicast_base = int(self.handle.multicast_ptr or 0)
+                except Exception:
+                    self.multicast_base = 0
         if len(self.peer_bases) != self.world:
             raise RuntimeError("symmetric memory rendezvous returned %d peers for a world of %d" % (len(self.peer_bases), self.world))
 

@@ -186,13 +186,16 @@ class FusedMapper:
         a, st = self.arena, L.stream()
         cur, nxt = (self.step_count - 1) & 1, self.step_count & 1
         bases = (C.c_uint64 * a.world)(*a.peer_bases)
+        # in-switch reduction / multicast store (NVLS) pays from 4 GPUs on (measured on 8 x B200: 74 vs 115 us at 8 GPUs,
+        # 85 vs 88 us at 4, 99 vs 61 us at 2 for the 9.0 M-parameter grid); below that plain peer loads / stores
+        mc = a.multicast_base if a.world >= 4 else 0
         a.barrier()                                                  # every rank's gradients are complete
         L.call("mf_adam_step_sharded", bases, a.world, a.rank, a.offsets["p_grid"], a.offsets["g_grid%d" % cur],
                a.offsets["g_grid%d" % nxt], L.ptr(self.m_grid), L.ptr(self.v_grid), a.sizes["p_grid"],
-               float(self.lr_embed), 0.9, 0.99, 1e-15, 0.0, self.step_count, st)
+               float(self.lr_embed), 0.9, 0.99, 1e-15, 0.0, self.step_count, mc, st)
         L.call("mf_adam_step_sharded", bases, a.world, a.rank, a.offsets["p_mlp"], a.offsets["g_mlp%d" % cur],
                a.offsets["g_mlp%d" % nxt], L.ptr(self.m_mlp), L.ptr(self.v_mlp), a.sizes["p_mlp"],
-               float(self.lr_decoder), 0.9, 0.99, 1e-8, 1e-6, self.step_count, st)
+               float(self.lr_decoder), 0.9, 0.99, 1e-8, 1e-6, self.step_count, mc, st)
         a.barrier()                                                  # every slab has reached every replica
         self.g_grid, self.g_mlp = self._g_grid[nxt], self._g_mlp[nxt]
         L.call("mf_mlp_prepare", L.ptr(self.mlp), L.ptr(self.prep), st)

@@ -32,6 +32,7 @@ def _worker(rank, world, port, out):
         m = FusedMapper(H.cuda_model(cfg, H.state_of(of)), group=dist.group.WORLD, peer_memory=pm)
         assert (m.arena is not None) == pm
         mappers[name] = m
+    mappers["peer"].arena.world_for_test = world
     # (1) the update alone on identical, seeded per-rank gradients: the two routes must agree bit for bit at world 2
     gen = torch.Generator().manual_seed(100 + rank)
     gg = (torch.randn(mappers["nccl"].grid.numel(), generator=gen) * 1e-3).to(dev)
