@@ -17,7 +17,7 @@ from .decoder import _Workspace
 
 
 class FusedMapper:
-    def __init__(self, model, lr_decoder=None, lr_embed=None, group=None, peer_memory="auto"):
+    def __init__(self, model, lr_decoder=None, lr_embed=None, group=None, peer_memory="auto", multicast="auto"):
         self.model = model
         cfg = model.config
         self.dev = model._device
@@ -40,6 +40,7 @@ class FusedMapper:
         # the gradient all-reduce + Adam + parameter broadcast become one sharded kernel (mf_adam_step_sharded).
         # peer_memory: True (require), False (NCCL all-reduce + replicated Adam), "auto" (try, fall back to NCCL).
         self.arena = None
+        self.multicast = multicast                                   # "auto": from 4 GPUs on; True / False: force
         if self.world > 1 and peer_memory:
             try:
                 self._init_peer_arena()
@@ -188,7 +189,7 @@ class FusedMapper:
         bases = (C.c_uint64 * a.world)(*a.peer_bases)
         # in-switch reduction / multicast store (NVLS) pays from 4 GPUs on (measured on 8 x B200: 74 vs 115 us at 8 GPUs,
         # 85 vs 88 us at 4, 99 vs 61 us at 2 for the 9.0 M-parameter grid); below that plain peer loads / stores
-        mc = a.multicast_base if a.world >= 4 else 0
+        mc = a.multicast_base if (self.multicast is True or (self.multicast == "auto" and a.world >= 4)) else 0
         a.barrier()                                                  # every rank's gradients are complete
         L.call("mf_adam_step_sharded", bases, a.world, a.rank, a.offsets["p_grid"], a.offsets["g_grid%d" % cur],
                a.offsets["g_grid%d" % nxt], L.ptr(self.m_grid), L.ptr(self.v_grid), a.sizes["p_grid"],

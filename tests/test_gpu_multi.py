@@ -32,7 +32,8 @@ def _worker(rank, world, port, out):
         m = FusedMapper(H.cuda_model(cfg, H.state_of(of)), group=dist.group.WORLD, peer_memory=pm)
         assert (m.arena is not None) == pm
         mappers[name] = m
-    mappers["peer"].arena.world_for_test = world
+    if mappers["peer"].arena.multicast_base:                       # NVSwitch multicast (NVLS) variant of the same kernel
+        mappers["peer_mc"] = FusedMapper(H.cuda_model(cfg, H.state_of(of)), group=dist.group.WORLD, peer_memory=True, multicast=True)
     # (1) the update alone on identical, seeded per-rank gradients: the two routes must agree bit for bit at world 2
     gen = torch.Generator().manual_seed(100 + rank)
     gg = (torch.randn(mappers["nccl"].grid.numel(), generator=gen) * 1e-3).to(dev)
@@ -61,7 +62,10 @@ def _worker(rank, world, port, out):
     dist.all_gather(others, torch.from_numpy(g).to(dev))
     same = all(bool(torch.equal(o, others[0])) for o in others)
     if rank == 0:
-        np.savez(out, upd_grid_nccl=upd["nccl"][0], upd_grid_peer=upd["peer"][0], upd_mlp_nccl=upd["nccl"][1], upd_mlp_peer=upd["peer"][1],
+        extra = {}
+        if "peer_mc" in upd:
+            extra = dict(upd_grid_mc=upd["peer_mc"][0], upd_mlp_mc=upd["peer_mc"][1], loss_mc=res["peer_mc"][2])
+        np.savez(out, **extra, upd_grid_nccl=upd["nccl"][0], upd_grid_peer=upd["peer"][0], upd_mlp_nccl=upd["nccl"][1], upd_mlp_peer=upd["peer"][1],
                  cleared=np.array([upd["peer"][2], upd["peer"][3]]), loss_nccl=res["nccl"][2], loss_peer=res["peer"][2], same=np.array(same))
     dist.destroy_process_group()
 
@@ -77,5 +81,9 @@ def test_peer_memory_adam_matches_nccl_route(tmp_path):
     np.testing.assert_array_equal(r["upd_grid_peer"], r["upd_grid_nccl"])
     np.testing.assert_array_equal(r["upd_mlp_peer"], r["upd_mlp_nccl"])
     assert r["cleared"].max() == 0.0
+    if "upd_grid_mc" in r:
+        np.testing.assert_array_equal(r["upd_grid_mc"], r["upd_grid_nccl"])
+        np.testing.assert_array_equal(r["upd_mlp_mc"], r["upd_mlp_nccl"])
+        np.testing.assert_allclose(r["loss_mc"], r["loss_nccl"], rtol=2e-3)
     # whole steps: the scatter order of the grid gradient is not deterministic, so only the losses are compared (fp32 tolerance)
     np.testing.assert_allclose(r["loss_peer"], r["loss_nccl"], rtol=2e-3)
