@@ -274,6 +274,7 @@ def run_gpu(args):
         also.update(tracking_bench(model, cfg, dev))
         also.update(frame_bench(dev))
         also.update(joint_query_bench(dev))
+        also.update(store_bench(mapper, dev, args.steps))
 
     if rank != 0:
         if world > 1:
@@ -372,6 +373,35 @@ def emit(obj):
 
 
 _REAL_STDOUT = 1
+
+def store_bench(mapper, dev, steps):
+    """Map step fed from the device-resident keyframe ray store (SURVEY 8 "next" row N1): 3584 rays sampled on the device
+    from 8 stored keyframes (150 x 200 rays each) + 512 rays of the current frame, ray generation, then the same step."""
+    import torch
+    import mipsfusion_b200 as mf
+    from mipsfusion_b200 import synth
+    cfg = {"sampling": {"kf_n_rays_h": 150, "kf_n_rays_w": 200}}
+    dirs = synth.camera_rays()
+    poses = synth.trajectory(8)
+    store = mf.KeyframeRayStore(cfg, dirs.shape[0], dirs.shape[1], 8, dev)
+    for k, c2w in enumerate(poses):
+        fr = synth.render_frame(c2w, dirs, seed=k)
+        store.add_keyframe({"direction": dirs, "rgb": fr["rgb"], "depth": fr["depth"], "frame_id": k})
+    poses_all = torch.stack(list(poses)).to(dev)
+    cur = store.rays[7, ::58][:512].contiguous()
+    related = list(range(8))
+    for _ in range(3):
+        mapper.step_from_store(store, 0, related, poses_all, R_RAYS - 512, cur_rays7=cur)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        losses = mapper.step_from_store(store, 0, related, poses_all, R_RAYS - 512, cur_rays7=cur)
+    float(losses[0])
+    dt = time.perf_counter() - t0
+    return {"store_fed_rays_per_s": R_RAYS * steps / dt,
+            "store_fed_shape": "KeyframeRayStore.sample_rays_in_submap (device draws, 8 keyframes) + 512 current-frame rays -> "
+                               "mf_gen_rays_packed -> map step; no host data per step"}
+
 
 def joint_query_bench(dev, res=512, n_submaps=16):
     """BASELINE configs[4] shape: joint SDF grid query at res^3 over n_submaps submaps (Mesher / render_mesh path):

@@ -220,6 +220,19 @@ int mf_gen_rays_packed(const float* rays7, const float* poses, const int64_t* po
 int mf_gen_rays_bwd(const float* dirs_cam, const int64_t* pose_idx, const float* d_rays_o, const float* d_rays_d,
                     float* d_poses, int64_t R, int K, void* stream);
 
+/* ---- N1 (first "next" row of SURVEY 8): keyframe ray store on the device (model/keyframeSet.py:25,76-79,170-175,386-437) ----
+ * mf_kf_store: add_keyframe -- store_slot (n_rays,7) = [dir_cam | rgb | depth] of the pixels (rows[j], cols[j]) of a
+ * full-resolution frame (dirs_cam (H*W,3), rgb (H*W,3), depth (H*W)); rows / cols = the uniform lattice (mf_sample_pixels_uniform). */
+int mf_kf_store(const float* dirs_cam, const float* rgb, const float* depth, const int64_t* rows, const int64_t* cols,
+                int img_w, int64_t n_rays, float* store_slot, void* stream);
+/* sample_rays_in_submap for given index draws (the reference's random.sample results, here device int64 arrays):
+ * store (num_kf, n_rays, 7); first / last keyframe ids, other_kf_ids (the related keyframes between them);
+ * out_rays7 (n,7), out_kf_ids (n), out_kf_indices (n) with n = n_first + n_other + n_last, in the reference's order. */
+int mf_kf_gather_rays(const float* store, int64_t n_rays, int64_t first_kf_id, const int64_t* other_kf_ids,
+                      int64_t last_kf_id, int n_related, const int64_t* idx_first, int64_t n_first,
+                      const int64_t* idx_other, int64_t n_other, const int64_t* idx_last, int64_t n_last,
+                      float* out_rays7, int64_t* out_kf_ids, int64_t* out_kf_indices, void* stream);
+
 /* ---- a13: RandomOptimizer particle scoring (RandomOptimizer.py:54-73,81-85,113-131) ----
  * particles6 (C_total,6) pre-sampled template; search_size (6), rot_cur (3,3), trans_cur (3) device;
  * dirs_cam (P,3) and target_d (P) are the sampled pixels.  c_begin/c_count select this rank's candidate

@@ -85,6 +85,8 @@ PROTOTYPES = {
     "mf_topk_workspace_size": (_L, [_L]),
     "mf_sample_pixels_topk": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "mf_gen_rays": (_I, [_P, _P, _P, _P, _P, _L, _I, _P]),
+    "mf_kf_store": (_I, [_P, _P, _P, _P, _P, _I, _L, _P, _P]),
+    "mf_kf_gather_rays": (_I, [_P, _L, _L, _P, _L, _I, _P, _L, _P, _L, _P, _L, _P, _P, _P, _P]),
     "mf_gen_rays_packed": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
     "mf_gen_rays_bwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _P]),
     "mf_ro_score": (_I, [_P, _P, _P, _P, _P, _P, C.POINTER(Field), _D, _D, _I, _I, _I, _P, _P, _P, _P, _P]),

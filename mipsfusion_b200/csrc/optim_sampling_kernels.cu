@@ -388,3 +388,72 @@ MF_API int mf_sample_pixels_topk(const float* depth, const float* keys, int img_
     MF_LAUNCH_CHECK();
     return MF_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// N1: keyframe ray store on the device (model/keyframeSet.py:25,76-79,170-175,386-455).
+// store (num_kf, n_rays, 7) fp32 = [dir_cam | rgb | depth] of the lattice-downsampled keyframes.
+// ---------------------------------------------------------------------------------------------
+// add_keyframe: rows of the full-resolution frame picked by the uniform lattice (pixel index = row * W + col)
+__global__ void kf_store_kernel(const float* __restrict__ dirs, const float* __restrict__ rgb, const float* __restrict__ depth,
+                                const int64_t* __restrict__ rows, const int64_t* __restrict__ cols, int img_w, int64_t n_rays,
+                                float* __restrict__ slot) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_rays) return;
+    const int64_t px = rows[j] * img_w + cols[j];
+    float* o = slot + j * 7;
+    o[0] = dirs[px * 3]; o[1] = dirs[px * 3 + 1]; o[2] = dirs[px * 3 + 2];
+    o[3] = rgb[px * 3]; o[4] = rgb[px * 3 + 1]; o[5] = rgb[px * 3 + 2];
+    o[6] = depth[px];
+}
+
+MF_API int mf_kf_store(const float* dirs_cam, const float* rgb, const float* depth, const int64_t* rows, const int64_t* cols,
+                       int img_w, int64_t n_rays, float* store_slot, void* stream) {
+    MF_CHECK_ARG(n_rays >= 0 && img_w > 0);
+    if (n_rays == 0) return MF_OK;
+    MF_CHECK_ARG(dirs_cam && rgb && depth && rows && cols && store_slot);
+    kf_store_kernel<<<(unsigned)((n_rays + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dirs_cam, rgb, depth, rows, cols, img_w, n_rays, store_slot);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}
+
+// sample_rays_in_submap (model/keyframeSet.py:386-437) for given index draws: output ray j comes from
+//   j <  n_first                : keyframe first_kf_id, ray idx_first[j]               -> kf_index 0
+//   j <  n_first + n_other      : idx = idx_other[.]: keyframe other_ids[idx / n_rays], ray idx % n_rays -> kf_index idx / n_rays + 1
+//   else                        : keyframe last_kf_id, ray idx_last[.]                 -> kf_index n_related - 1
+// other_ids = related_kf_ids + 1 (n_other_kf entries).  Integer outputs are exactly the reference's.
+__global__ void kf_gather_kernel(const float* __restrict__ store, int64_t n_rays, int64_t first_kf_id,
+                                 const int64_t* __restrict__ other_ids, int64_t last_kf_id, int n_related,
+                                 const int64_t* __restrict__ idx_first, int64_t n_first, const int64_t* __restrict__ idx_other,
+                                 int64_t n_other, const int64_t* __restrict__ idx_last, int64_t n_last,
+                                 float* __restrict__ out, int64_t* __restrict__ kf_ids, int64_t* __restrict__ kf_indices) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_first + n_other + n_last) return;
+    int64_t kf, ray, kidx;
+    if (j < n_first) { kf = first_kf_id; ray = idx_first[j]; kidx = 0; }
+    else if (j < n_first + n_other) {
+        const int64_t idx = idx_other[j - n_first], local = idx / n_rays;
+        kf = other_ids[local]; ray = idx - local * n_rays; kidx = local + 1;
+    } else { kf = last_kf_id; ray = idx_last[j - n_first - n_other]; kidx = n_related - 1; }
+    const float* src = store + (kf * n_rays + ray) * 7;
+    float* o = out + j * 7;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) o[k] = src[k];
+    kf_ids[j] = kf; kf_indices[j] = kidx;
+}
+
+MF_API int mf_kf_gather_rays(const float* store, int64_t n_rays, int64_t first_kf_id, const int64_t* other_kf_ids,
+                             int64_t last_kf_id, int n_related, const int64_t* idx_first, int64_t n_first,
+                             const int64_t* idx_other, int64_t n_other, const int64_t* idx_last, int64_t n_last,
+                             float* out_rays7, int64_t* out_kf_ids, int64_t* out_kf_indices, void* stream) {
+    MF_CHECK_ARG(n_rays > 0 && n_related >= 1 && n_first >= 0 && n_other >= 0 && n_last >= 0);
+    const int64_t n = n_first + n_other + n_last;
+    if (n == 0) return MF_OK;
+    MF_CHECK_ARG(store && out_rays7 && out_kf_ids && out_kf_indices);
+    MF_CHECK_ARG((n_first == 0 || idx_first) && (n_other == 0 || (idx_other && other_kf_ids)) && (n_last == 0 || idx_last));
+    kf_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(store, n_rays, first_kf_id, other_kf_ids, last_kf_id,
+                                                                                  n_related, idx_first, n_first, idx_other, n_other,
+                                                                                  idx_last, n_last, out_rays7, out_kf_ids, out_kf_indices);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}

@@ -169,6 +169,24 @@ class FusedMapper:
         torch.cuda.current_stream(self.dev).synchronize()
         return hb["out"]
 
+    def step_from_store(self, store, first_kf_Id, related_kf_ids, poses_all, pix_num, cur_rays7=None, EMD_w=0.01, **draws):
+        """One mapping iteration fed from the device-resident keyframe ray store (steps 3.1-3.4 of the reference's BA
+        loop, mipsfusion.py:293-335, without any host data): sample ``pix_num`` rays of the submap's keyframes
+        (:class:`KeyframeRayStore.sample_rays_in_submap`), append the current frame's rays ``cur_rays7`` (n,7; pose index
+        -1 = last pose), generate the rays with ``poses_all`` (K,4,4) and run :meth:`step`.  Returns the device losses."""
+        rays, _, kf_indices = store.sample_rays_in_submap(first_kf_Id, related_kf_ids, pix_num, **draws)
+        if cur_rays7 is not None:
+            rays = torch.cat([rays, cur_rays7.to(self.dev, torch.float32)], 0)
+            kf_indices = torch.cat([kf_indices, torch.full((cur_rays7.shape[0],), -1, device=self.dev, dtype=torch.int64)], 0)
+        R = rays.shape[0]
+        f32 = dict(device=self.dev, dtype=torch.float32)
+        o, d, rgb, depth = torch.empty(R, 3, **f32), torch.empty(R, 3, **f32), torch.empty(R, 3, **f32), torch.empty(R, **f32)
+        poses = poses_all.to(self.dev, torch.float32).contiguous()
+        L.call("mf_gen_rays_packed", L.ptr(rays), L.ptr(poses), L.ptr(kf_indices), L.ptr(o), L.ptr(d), L.ptr(rgb), L.ptr(depth), R,
+               poses.shape[0], L.stream())
+        self.launches += 2
+        return self.step(o, d, rgb, depth, EMD_w=EMD_w)
+
     def apply_gradients(self):
         """Adam on (grid, decoder) with the reference's groups (mipsfusion.py:580-584), zero_grad fused in."""
         self.step_count += 1

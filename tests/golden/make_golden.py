@@ -214,7 +214,54 @@ def gen_blend():
                         dist_weight=ref_mh.convert_dist_to_weight(dist))
 
 
+def gen_keyframes():
+    """The reference's own KeyframeSet (ray part) with python random.sample patched to replay recorded draws."""
+    import random as pyrandom
+    from model import keyframeSet as ref_kf
+    g = torch.Generator().manual_seed(77)
+    H, W, nh, nw, num_kf = 48, 64, 6, 8, 6
+    ks = object.__new__(ref_kf.KeyframeSet)                      # the constructor needs the whole SLAM config; only the ray part is used
+    ks.H, ks.W, ks.n_rays_h, ks.n_rays_w = H, W, nh, nw
+    ks.num_rays_to_save = nh * nw
+    ks.row_indices, ks.col_indices = ref_samp.sample_pixels_uniformly(H, W, nh, nw)
+    ks.rays = torch.zeros((num_kf, ks.num_rays_to_save, 7))
+    ks.frame_ids = None
+    frames = []
+    for k in range(num_kf):
+        batch = {"direction": torch.randn(1, H, W, 3, generator=g), "rgb": torch.rand(1, H, W, 3, generator=g),
+                 "depth": torch.rand(1, H, W, generator=g) * 4, "frame_id": 5 * k}
+        ks.add_keyframe(batch)
+        frames.append(batch)
+    out = {"H": H, "W": W, "nh": nh, "nw": nw, "store": ks.rays.numpy(),
+           "direction": torch.stack([f["direction"][0] for f in frames]).numpy(), "rgb": torch.stack([f["rgb"][0] for f in frames]).numpy(),
+           "depth": torch.stack([f["depth"][0] for f in frames]).numpy()}
+    draws = []
+    real_sample = pyrandom.sample
+    def recording_sample(population, k):
+        r = real_sample(population, k); draws.append(r); return r
+    ref_kf.random.sample = recording_sample
+    pyrandom.seed(1234)
+    cases = [("one", 2, [2], 20), ("two", 1, [1, 4], 30), ("many", 0, [0, 2, 3, 5], 37), ("five", 1, [1, 0, 2, 3, 4, 5], 64)]
+    for name, first, related, pix in cases:
+        draws.clear()
+        rays, kf_ids, kf_indices = ks.sample_rays_in_submap(torch.tensor(first), torch.tensor(related), pix)
+        out[f"{name}:first"] = first; out[f"{name}:related"] = np.array(related); out[f"{name}:pix"] = pix
+        for i, d in enumerate(draws):
+            out[f"{name}:draw{i}"] = np.array(d, dtype=np.int64)
+        out[f"{name}:n_draws"] = len(draws)
+        out[f"{name}:rays"] = rays.numpy(); out[f"{name}:kf_ids"] = kf_ids.numpy(); out[f"{name}:kf_indices"] = kf_indices.numpy()
+    draws.clear()
+    rays, kf_ids, kf_indices = ks.sample_rays_in_given_kf(torch.tensor([4, 1, 3]), 25)
+    out["given:ids"] = np.array([4, 1, 3]); out["given:draw"] = np.array(draws[0], dtype=np.int64)
+    out["given:rays"] = rays.numpy(); out["given:kf_ids"] = kf_ids.numpy(); out["given:kf_indices"] = kf_indices.numpy()
+    ref_kf.random.sample = real_sample
+    np.savez_compressed(os.path.join(OUT, "keyframes.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "keyframes":
+        gen_keyframes(); sys.exit(0)
+    gen_keyframes()
     gen_lattice(); gen_sampling(); gen_losses(); gen_decoder()
     cfg, model = gen_scene()
     gen_ro(cfg, model)

@@ -208,3 +208,55 @@ def test_fused_mapper_matches_oracle_and_host_route():
     a = m_dev2.step(*dargs).cpu().numpy().copy()
     b = m_host2.step_host(rays7.pin_memory(), pose_idx.pin_memory(), poses.cuda()).numpy().copy()
     np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("N,pattern", [(1, "all"), (1025, "all"), (1500, "none"), (2500, "mixed"), (128, "last")])
+def test_backward_active_point_list_edge_cases(N, pattern, impl):
+    """The backward visits only the rows of the upstream gradient that are non-zero.  Edge cases of that work list
+    (empty list, full list, block / tile boundaries, a single active row) against the oracle, both decoders;
+    skipped points get an exactly zero dL/dp and all-zero upstream gradients give exactly zero parameter gradients."""
+    from mipsfusion_b200 import _lib as L
+    cfg = H.make_config(12)
+    of = H.oracle_field(cfg, grid_scale=0.3, seed=5)
+    model = H.cuda_model(cfg, H.state_of(of))
+    g = torch.Generator().manual_seed(N)
+    bb = torch.tensor(cfg["mapping"]["bound"], dtype=torch.float32)
+    pts = bb[:, 0] + (bb[:, 1] - bb[:, 0]) * torch.rand(N, 3, generator=g)
+    G = torch.randn(N, 10, generator=g)
+    keep = torch.ones(N, dtype=torch.bool)
+    if pattern == "none":
+        keep[:] = False
+    elif pattern == "mixed":
+        keep = torch.rand(N, generator=g) < 0.4
+        keep[1024:2048] = False                                        # one compaction block without any active row
+    elif pattern == "last":
+        keep[:] = False; keep[-1] = True
+    G = G * keep[:, None]
+    po = pts.clone().requires_grad_(True)
+    of.run_network(po).backward(G)
+    # impl 1: fp32 decoder, points require grad (dL/dp checked); impl 0: tcgen05 decoder, parameter gradients only
+    # (points with requires_grad always route through the fp32 decoder, DESIGN.md section 2)
+    want_dp = impl == 1
+    L.call("mf_set_decoder_impl", impl)
+    try:
+        pc = pts.cuda().requires_grad_(want_dp)
+        model.run_network(pc).backward(G.cuda())
+        torch.cuda.synchronize()
+    finally:
+        L.call("mf_set_decoder_impl", 0)
+    gg = model.embed_fn.params.grad.cpu()
+    gp = pc.grad.cpu() if want_dp else None
+    if want_dp:
+        assert bool((gp[~keep] == 0).all())
+    if pattern == "none":
+        assert float(gg.abs().max()) == 0.0 and (gp is None or float(gp.abs().max()) == 0.0)
+        assert all(float(p.grad.abs().max()) == 0.0 for p in model.decoder.parameters())
+        return
+    tol = 1e-4 if impl == 1 else 2e-3              # fp32 decoder / tcgen05 decoder (bf16 x 3): parameter gradients
+    assert H.rel_err(gg, of.grid.grad) < tol
+    for name, p in model.decoder.named_parameters():
+        assert H.rel_err(p.grad.cpu(), of.w[name].grad) < tol, name
+    if want_dp:
+        assert H.rel_err(gp, po.grad) < 1e-3
