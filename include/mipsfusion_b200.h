@@ -233,6 +233,15 @@ int mf_kf_gather_rays(const float* store, int64_t n_rays, int64_t first_kf_id, c
                       const int64_t* idx_other, int64_t n_other, const int64_t* idx_last, int64_t n_last,
                       float* out_rays7, int64_t* out_kf_ids, int64_t* out_kf_indices, void* stream);
 
+/* Sampling without replacement on the device (the reference's python random.sample(range(n), k)): out[j] = perm(j), perm a
+ * keyed pseudo-random permutation of [0, n) (4-round Feistel network + cycle walking; oracle/keyframes.py restates it). */
+int mf_sample_distinct(int64_t n, int64_t k, uint32_t seed, int64_t* out, void* stream);
+/* sample_rays_in_submap with the draws made inside the kernel (segment seeds seed, seed+1, seed+2 for the first / other /
+ * latest keyframes); out_idx (optional) receives the drawn indices, the other outputs are as mf_kf_gather_rays. */
+int mf_kf_sample_rays(const float* store, int64_t n_rays, int64_t first_kf_id, const int64_t* other_kf_ids, int64_t n_other_kf,
+                      int64_t last_kf_id, int n_related, int64_t n_first, int64_t n_other, int64_t n_last, uint32_t seed,
+                      float* out_rays7, int64_t* out_kf_ids, int64_t* out_kf_indices, int64_t* out_idx, void* stream);
+
 /* ---- a13: RandomOptimizer particle scoring (RandomOptimizer.py:54-73,81-85,113-131) ----
  * particles6 (C_total,6) pre-sampled template; search_size (6), rot_cur (3,3), trans_cur (3) device;
  * dirs_cam (P,3) and target_d (P) are the sampled pixels.  c_begin/c_count select this rank's candidate

@@ -87,6 +87,8 @@ PROTOTYPES = {
     "mf_gen_rays": (_I, [_P, _P, _P, _P, _P, _L, _I, _P]),
     "mf_kf_store": (_I, [_P, _P, _P, _P, _P, _I, _L, _P, _P]),
     "mf_kf_gather_rays": (_I, [_P, _L, _L, _P, _L, _I, _P, _L, _P, _L, _P, _L, _P, _P, _P, _P]),
+    "mf_sample_distinct": (_I, [_L, _L, C.c_uint32, _P, _P]),
+    "mf_kf_sample_rays": (_I, [_P, _L, _L, _P, _L, _L, _I, _L, _L, _L, C.c_uint32, _P, _P, _P, _P, _P]),
     "mf_gen_rays_packed": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
     "mf_gen_rays_bwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _P]),
     "mf_ro_score": (_I, [_P, _P, _P, _P, _P, _P, C.POINTER(Field), _D, _D, _I, _I, _I, _P, _P, _P, _P, _P]),

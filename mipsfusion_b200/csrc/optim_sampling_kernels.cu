@@ -457,3 +457,94 @@ MF_API int mf_kf_gather_rays(const float* store, int64_t n_rays, int64_t first_k
     MF_LAUNCH_CHECK();
     return MF_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Sampling without replacement on the device (python random.sample(range(n), k) in the reference): element j of the
+// sample is perm(j), where perm is a keyed pseudo-random PERMUTATION of [0, n): a 4-round balanced Feistel network on
+// 2b bits (4^b >= n) with cycle walking.  O(k) work, no sort, k distinct values by construction; oracle/keyframes.py
+// restates it in numpy (bit-exact).  mix32 = the public-domain "lowbias32" integer hash.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline uint32_t mf_mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+__host__ __device__ inline int mf_feistel_half_bits(uint64_t n) {
+    int b = 1;
+    while (((uint64_t)1 << (2 * b)) < n) ++b;
+    return b;
+}
+__host__ __device__ inline uint64_t mf_feistel_perm(uint64_t j, uint64_t n, int b, uint32_t seed) {
+    const uint32_t mask = (uint32_t)(((uint64_t)1 << b) - 1);
+    uint64_t x = j;
+    do {
+        uint32_t l = (uint32_t)(x >> b) & mask, r = (uint32_t)x & mask;
+#pragma unroll
+        for (int round = 0; round < 4; ++round) {
+            const uint32_t key = mf_mix32(seed + 0x9e3779b9U * (uint32_t)(round + 1));
+            const uint32_t t = l ^ (mf_mix32(r ^ key) & mask);
+            l = r; r = t;
+        }
+        x = ((uint64_t)l << b) | r;
+    } while (x >= n);
+    return x;
+}
+
+__global__ void sample_distinct_kernel(int64_t n, int64_t k, uint32_t seed, int64_t* __restrict__ out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    out[j] = (int64_t)mf_feistel_perm((uint64_t)j, (uint64_t)n, mf_feistel_half_bits((uint64_t)n), seed);
+}
+
+MF_API int mf_sample_distinct(int64_t n, int64_t k, uint32_t seed, int64_t* out, void* stream) {
+    MF_CHECK_ARG(n >= 1 && k >= 0 && k <= n && n <= ((int64_t)1 << 40));
+    if (k == 0) return MF_OK;
+    MF_CHECK_ARG(out);
+    sample_distinct_kernel<<<(unsigned)((k + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, k, seed, out);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}
+
+// sample_rays_in_submap with the draws made in the kernel: segment s uses seed + s (first, other, last)
+__global__ void kf_sample_kernel(const float* __restrict__ store, int64_t n_rays, int64_t first_kf_id,
+                                 const int64_t* __restrict__ other_ids, int64_t n_other_kf, int64_t last_kf_id, int n_related,
+                                 int64_t n_first, int64_t n_other, int64_t n_last, uint32_t seed,
+                                 float* __restrict__ out, int64_t* __restrict__ kf_ids, int64_t* __restrict__ kf_indices,
+                                 int64_t* __restrict__ out_idx) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_first + n_other + n_last) return;
+    int64_t kf, ray, kidx, idx;
+    if (j < n_first) {
+        idx = (int64_t)mf_feistel_perm((uint64_t)j, (uint64_t)n_rays, mf_feistel_half_bits((uint64_t)n_rays), seed);
+        kf = first_kf_id; ray = idx; kidx = 0;
+    } else if (j < n_first + n_other) {
+        const uint64_t pop = (uint64_t)(n_other_kf * n_rays);
+        idx = (int64_t)mf_feistel_perm((uint64_t)(j - n_first), pop, mf_feistel_half_bits(pop), seed + 1u);
+        const int64_t local = idx / n_rays;
+        kf = other_ids[local]; ray = idx - local * n_rays; kidx = local + 1;
+    } else {
+        idx = (int64_t)mf_feistel_perm((uint64_t)(j - n_first - n_other), (uint64_t)n_rays, mf_feistel_half_bits((uint64_t)n_rays), seed + 2u);
+        kf = last_kf_id; ray = idx; kidx = n_related - 1;
+    }
+    const float* src = store + (kf * n_rays + ray) * 7;
+    float* o = out + j * 7;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) o[k] = src[k];
+    kf_ids[j] = kf; kf_indices[j] = kidx;
+    if (out_idx) out_idx[j] = idx;
+}
+
+MF_API int mf_kf_sample_rays(const float* store, int64_t n_rays, int64_t first_kf_id, const int64_t* other_kf_ids, int64_t n_other_kf,
+                             int64_t last_kf_id, int n_related, int64_t n_first, int64_t n_other, int64_t n_last, uint32_t seed,
+                             float* out_rays7, int64_t* out_kf_ids, int64_t* out_kf_indices, int64_t* out_idx, void* stream) {
+    MF_CHECK_ARG(n_rays > 0 && n_related >= 1 && n_first >= 0 && n_other >= 0 && n_last >= 0 && n_other_kf >= 0);
+    MF_CHECK_ARG(n_first <= n_rays && n_last <= n_rays && n_other <= n_other_kf * n_rays);
+    const int64_t n = n_first + n_other + n_last;
+    if (n == 0) return MF_OK;
+    MF_CHECK_ARG(store && out_rays7 && out_kf_ids && out_kf_indices && (n_other == 0 || other_kf_ids));
+    kf_sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(store, n_rays, first_kf_id, other_kf_ids, n_other_kf,
+                                                                                  last_kf_id, n_related, n_first, n_other, n_last, seed,
+                                                                                  out_rays7, out_kf_ids, out_kf_indices, out_idx);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}

@@ -110,7 +110,38 @@ class MLP_reg(nn.Module):
     def __getstate__(self):
         s = self.__dict__.copy()
         s.pop("_prep_cache", None)
+        s.pop("_flat_grad", None)
         return s
+
+    def flat_grad_target(self):
+        """Flat (MF_MLP_PARAMS) gradient buffer the backward kernels can accumulate into directly, or None.
+
+        The ten parameter ``.grad`` tensors are kept as views of one flat buffer (the layout of the kernels' gradient
+        blob), so a backward pass adds into it in place instead of returning ten tensors that autograd then adds one by
+        one.  Usable when every ``.grad`` is None (fresh / after ``zero_grad(set_to_none=True)``: the buffer is cleared
+        and the views installed) or already is the matching view; any other state (grads assigned by the user, a copied
+        module) returns None and the caller falls back to returning gradients."""
+        ps = self.ordered_params()
+        dev = ps[0].device
+        flat = self.__dict__.get("_flat_grad")
+        if flat is None or flat.device != dev:
+            flat = torch.zeros(L.MF_MLP_PARAMS, device=dev, dtype=torch.float32)
+            self.__dict__["_flat_grad"] = flat
+        if all(p.grad is None for p in ps):
+            flat.zero_()
+            o = 0
+            for p in ps:
+                n = p.numel()
+                p.grad = flat[o:o + n].view(p.shape)
+                o += n
+            return flat
+        o, base = 0, flat.data_ptr()
+        for p in ps:
+            g = p.grad
+            if g is None or g.data_ptr() != base + 4 * o or g.shape != p.shape or not g.is_contiguous() or g.dtype != torch.float32:
+                return None
+            o += p.numel()
+        return flat
 
 
     def forward(self, embed, embed_pos, query_pts):

@@ -13,15 +13,25 @@ from . import _lib as L
 from . import sampling_helper as sh
 
 
-def sample_without_replacement(n, k, device, keys=None):
-    """k distinct indices of range(n) in random order (python ``random.sample(range(n), k)``): the indices of the k
-    largest of n uniform keys (ties: lower index first), selected by the radix top-k kernel of the pixel samplers."""
+def _new_seed():
+    return int(torch.randint(0, 2 ** 31 - 1, (1,)))            # torch's CPU generator: torch.manual_seed makes runs repeatable
+
+
+def sample_without_replacement(n, k, device, keys=None, seed=None):
+    """k distinct indices of range(n) in random order (python ``random.sample(range(n), k)``).
+
+    Default: element j is perm(j) for a keyed pseudo-random permutation of range(n) (``mf_sample_distinct``: Feistel
+    network + cycle walking, O(k), seeded from torch's CPU generator unless ``seed`` is given).  With explicit ``keys``
+    (n floats): the indices of the k largest keys (ties: lower index first) through the radix top-k kernel."""
     if k < 0 or k > n:
         raise ValueError("sample larger than population or is negative")          # python random.sample's own error
     if k == 0:
         return torch.empty(0, device=device, dtype=torch.int64)
     if keys is None:
-        keys = torch.rand(n, device=device, dtype=torch.float32)
+        out = torch.empty(k, device=device, dtype=torch.int64)
+        with torch.cuda.device(device):
+            L.call("mf_sample_distinct", n, k, (_new_seed() if seed is None else int(seed)) & 0xffffffff, L.ptr(out), L.stream())
+        return out
     if k > 4096:                                  # beyond the selection kernel's single-CTA sort (never reached by the shipped configs)
         return torch.argsort(keys.to(device), descending=True, stable=True)[:k]
     ones = torch.ones(1, n, device=device, dtype=torch.float32)
@@ -70,15 +80,34 @@ class KeyframeRayStore:
         last = max(pix_num // related_kf_num, pix_num // 5)
         return first, pix_num - first - last, last
 
-    def sample_rays_in_submap(self, first_kf_Id, related_kf_ids, pix_num, idx_first=None, idx_other=None, idx_last=None):
+    def sample_rays_in_submap(self, first_kf_Id, related_kf_ids, pix_num, idx_first=None, idx_other=None, idx_last=None,
+                              seed=None, out=None, return_draws=False):
         """-> sampled_rays (n,7), kf_ids (n,), kf_indices (n,) on the device, in the reference's order (first keyframe,
-        other related keyframes, latest keyframe).  idx_* : explicit index draws (int64), drawn on the device when None."""
+        other related keyframes, latest keyframe).  idx_* : explicit index draws (int64); without them the draws are
+        made inside the gather kernel (one launch; ``seed`` fixes them, ``return_draws`` also returns the indices).
+        ``out``: optional (>= n, 7) device buffer that receives the rays."""
         dev = self.device
         related = torch.as_tensor(related_kf_ids, dtype=torch.int64).reshape(-1)
         n_rel = int(related.shape[0])
         n_first, n_other, n_last = self.split_counts(int(pix_num), n_rel)
         nr = self.num_rays_to_save
         other_ids = related[1:-1] if n_rel > 2 else related[1:]
+        if idx_first is None and idx_other is None and idx_last is None:
+            n = n_first + n_other + n_last
+            rays = torch.empty(n, 7, device=dev, dtype=torch.float32) if out is None else out[:n]
+            kf_ids = torch.empty(n, device=dev, dtype=torch.int64); kf_indices = torch.empty_like(kf_ids)
+            draws = torch.empty(n, device=dev, dtype=torch.int64) if return_draws else None
+            key = tuple(int(v) for v in other_ids)
+            cache = self.__dict__.setdefault("_ids_cache", {})
+            other_d = cache.get(key)
+            if other_d is None:
+                other_d = cache[key] = other_ids.to(dev).contiguous()
+            with torch.cuda.device(dev):
+                L.call("mf_kf_sample_rays", L.ptr(self.rays), nr, int(first_kf_Id), L.ptr(other_d) if n_other else None,
+                       int(other_ids.shape[0]), int(related[-1]), n_rel, n_first, n_other, n_last,
+                       (_new_seed() if seed is None else int(seed)) & 0xffffffff, L.ptr(rays), L.ptr(kf_ids), L.ptr(kf_indices),
+                       L.ptr(draws), L.stream())
+            return (rays, kf_ids, kf_indices, draws) if return_draws else (rays, kf_ids, kf_indices)
         if idx_first is None:
             idx_first = sample_without_replacement(nr, n_first, dev)
         if n_other and idx_other is None:

@@ -174,18 +174,26 @@ class FusedMapper:
         loop, mipsfusion.py:293-335, without any host data): sample ``pix_num`` rays of the submap's keyframes
         (:class:`KeyframeRayStore.sample_rays_in_submap`), append the current frame's rays ``cur_rays7`` (n,7; pose index
         -1 = last pose), generate the rays with ``poses_all`` (K,4,4) and run :meth:`step`.  Returns the device losses."""
-        rays, _, kf_indices = store.sample_rays_in_submap(first_kf_Id, related_kf_ids, pix_num, **draws)
-        if cur_rays7 is not None:
-            rays = torch.cat([rays, cur_rays7.to(self.dev, torch.float32)], 0)
-            kf_indices = torch.cat([kf_indices, torch.full((cur_rays7.shape[0],), -1, device=self.dev, dtype=torch.int64)], 0)
-        R = rays.shape[0]
-        f32 = dict(device=self.dev, dtype=torch.float32)
-        o, d, rgb, depth = torch.empty(R, 3, **f32), torch.empty(R, 3, **f32), torch.empty(R, 3, **f32), torch.empty(R, **f32)
-        poses = poses_all.to(self.dev, torch.float32).contiguous()
-        L.call("mf_gen_rays_packed", L.ptr(rays), L.ptr(poses), L.ptr(kf_indices), L.ptr(o), L.ptr(d), L.ptr(rgb), L.ptr(depth), R,
-               poses.shape[0], L.stream())
+        n_cur = 0 if cur_rays7 is None else int(cur_rays7.shape[0])
+        R = int(pix_num) + n_cur
+        sb = self._bufs.get(("store", R))
+        if sb is None:
+            f32 = dict(device=self.dev, dtype=torch.float32)
+            sb = dict(rays7=torch.empty(R, 7, **f32), idx=torch.full((R,), -1, device=self.dev, dtype=torch.int64),
+                      o=torch.empty(R, 3, **f32), d=torch.empty(R, 3, **f32), rgb=torch.empty(R, 3, **f32), depth=torch.empty(R, **f32))
+            self._bufs[("store", R)] = sb
+        rays, _, kf_indices = store.sample_rays_in_submap(first_kf_Id, related_kf_ids, pix_num, out=sb["rays7"], **draws)[:3]
+        if rays.data_ptr() != sb["rays7"].data_ptr():               # explicit draws: gathered into a fresh tensor
+            sb["rays7"][:pix_num].copy_(rays)
+        sb["idx"][:pix_num].copy_(kf_indices)                       # the tail stays -1: current frame = last pose
+        if n_cur:
+            sb["rays7"][pix_num:].copy_(cur_rays7)
+        poses = poses_all if (poses_all.is_cuda and poses_all.dtype == torch.float32 and poses_all.is_contiguous()) \
+            else poses_all.to(self.dev, torch.float32).contiguous()
+        L.call("mf_gen_rays_packed", L.ptr(sb["rays7"]), L.ptr(poses), L.ptr(sb["idx"]), L.ptr(sb["o"]), L.ptr(sb["d"]), L.ptr(sb["rgb"]),
+               L.ptr(sb["depth"]), R, poses.shape[0], L.stream())
         self.launches += 2
-        return self.step(o, d, rgb, depth, EMD_w=EMD_w)
+        return self.step(sb["o"], sb["d"], sb["rgb"], sb["depth"], EMD_w=EMD_w)
 
     def apply_gradients(self):
         """Adam on (grid, decoder) with the reference's groups (mipsfusion.py:580-584), zero_grad fused in."""

@@ -49,14 +49,14 @@ class _FieldQueryFn(torch.autograd.Function):
         model = ctx.model
         field = model._field(ctx.keep, impl=ctx.impl)
         N = pts.shape[0]
-        g_grid = torch.zeros_like(grid)
-        g_mlp = torch.zeros(L.MF_MLP_PARAMS, device=pts.device, dtype=torch.float32)
+        g_grid, ret_grid, g_mlp, ret_mlp = _grad_targets(model, grid, pts.device, ctx.needs_input_grad[3], all(ctx.needs_input_grad[4:]))
         d_pts = torch.empty_like(pts) if ctx.needs_input_grad[0] else None
         d_out = d_out.contiguous()                     # bound to a name: a temporary could be recycled before the launch
         ws = _Workspace.get(pts.device, field_points=N)
         L.call("mf_field_query_bwd", L.ptr(pts), C.byref(field), int(ctx.normalize), L.ptr(d_out), L.ptr(g_grid),
                L.ptr(g_mlp), L.ptr(d_pts), L.ptr(ws), N, L.stream())
-        return (d_pts, None, None, g_grid, *_split(g_mlp, ctx.shapes))
+        mlp_grads = _split(g_mlp, ctx.shapes) if ret_mlp else [None] * len(ctx.shapes)
+        return (d_pts, None, None, g_grid if ret_grid else None, *mlp_grads)
 
 
 def _split(flat, shapes):
@@ -66,6 +66,26 @@ def _split(flat, shapes):
         out.append(flat[o:o + n].view(shp))
         o += n
     return out
+
+
+def _grad_targets(model, grid, dev, need_grid, need_mlp):
+    """Where the backward kernels accumulate: straight into the parameters' ``.grad`` when that is possible (saves the
+    zero-fill of a 36 MB temporary plus autograd's add into ``.grad``, and ten small adds for the decoder), else into fresh
+    tensors that are returned to autograd.  ``loss.backward()`` sees no difference; set
+    ``model.accumulate_grads_in_place = False`` when gradients are taken with ``torch.autograd.grad`` (which must not
+    touch ``.grad``).  -> (g_grid, return_grid, g_mlp, return_mlp)"""
+    in_place = getattr(model, "accumulate_grads_in_place", True)
+    p = model.embed_fn.params
+    g = p.grad if (in_place and need_grid and p.data_ptr() == grid.data_ptr()) else None
+    if g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == grid.shape and g.device == grid.device \
+            and g.data_ptr() % 16 == 0:
+        g_grid, ret_grid = g, False
+    else:
+        g_grid, ret_grid = torch.zeros_like(grid), True
+    flat = model.decoder.flat_grad_target() if (in_place and need_mlp) else None
+    if flat is not None:
+        return g_grid, ret_grid, flat, False
+    return g_grid, ret_grid, torch.zeros(L.MF_MLP_PARAMS, device=dev, dtype=torch.float32), True
 
 
 class _RenderFn(torch.autograd.Function):
@@ -125,14 +145,14 @@ class _RenderFn(torch.autograd.Function):
         if g_raw is not None:
             d_raw = d_raw + g_raw
         want_rays = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        g_grid = torch.zeros_like(grid)
-        g_mlp = torch.zeros(L.MF_MLP_PARAMS, device=dev, dtype=torch.float32)
+        g_grid, ret_grid, g_mlp, ret_mlp = _grad_targets(model, grid, dev, ctx.needs_input_grad[7], all(ctx.needs_input_grad[8:]))
         d_o = torch.empty_like(rays_o) if want_rays else None
         d_d = torch.empty_like(rays_d) if want_rays else None
         ws = _Workspace.get(dev, field_points=R * S, want_ray_grads=want_rays)
         L.call("mf_field_query_rays_bwd", L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), C.byref(field), L.ptr(d_raw), L.ptr(ctx.feat),
                L.ptr(g_grid), L.ptr(g_mlp), L.ptr(d_o), L.ptr(d_d), L.ptr(ws), R, S, st)
-        return (d_o, d_d, None, None, None, None, None, g_grid, *_split(g_mlp, ctx.shapes))
+        mlp_grads = _split(g_mlp, ctx.shapes) if ret_mlp else [None] * len(ctx.shapes)
+        return (d_o, d_d, None, None, None, None, None, g_grid if ret_grid else None, *mlp_grads)
 
 
 class JointEncoding(nn.Module):

@@ -49,3 +49,41 @@ def sample_rays_in_given_kf(rays, given_kf_ids, idx):
     sampled = rays[given_kf_ids].reshape(-1, 7)[idx]                             # :451
     kf_indices = torch.div(idx, n_rays, rounding_mode="floor")
     return sampled, given_kf_ids[kf_indices], kf_indices
+
+
+# ---- device draws: keyed Feistel permutation (restates mf_feistel_perm of csrc/optim_sampling_kernels.cu; no reference
+# counterpart -- the reference calls python random.sample) ---------------------------------------------------------------
+def _mix32(x):
+    import numpy as np
+    x = np.asarray(x, dtype=np.uint32)
+    x = x ^ (x >> np.uint32(16)); x = (x * np.uint32(0x7feb352d)).astype(np.uint32)
+    x = x ^ (x >> np.uint32(15)); x = (x * np.uint32(0x846ca68b)).astype(np.uint32)
+    return x ^ (x >> np.uint32(16))
+
+
+def feistel_sample(n, k, seed):
+    """k distinct indices of range(n): out[j] = perm(j) (int64 numpy array)."""
+    import numpy as np
+    b = 1
+    while (1 << (2 * b)) < n:
+        b += 1
+    mask = np.uint32((1 << b) - 1)
+    out = np.empty(k, dtype=np.int64)
+    with np.errstate(over="ignore"):
+        keys = [_mix32(np.uint32((seed + 0x9e3779b9 * (r + 1)) & 0xffffffff)) for r in range(4)]
+        x = np.arange(k, dtype=np.uint64)
+        todo = np.ones(k, dtype=bool)
+        while todo.any():
+            xs = x[todo]
+            l = ((xs >> np.uint64(b)).astype(np.uint32)) & mask
+            r = xs.astype(np.uint32) & mask
+            for key in keys:
+                t = l ^ (_mix32(r ^ key) & mask)
+                l, r = r, t
+            xs = (l.astype(np.uint64) << np.uint64(b)) | r.astype(np.uint64)
+            x[todo] = xs
+            done_now = xs < np.uint64(n)
+            idxs = np.nonzero(todo)[0]
+            todo[idxs[done_now]] = False
+    out[:] = x.astype(np.int64)
+    return out

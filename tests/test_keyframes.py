@@ -114,3 +114,42 @@ def test_gpu_device_draws_and_store_fed_mapping_step():
     m2 = FusedMapper(H.cuda_model(cfg, H.state_of(of)))
     b = m2.step(rays_o.cuda().contiguous(), rays_d.cuda().contiguous(), rays[:, 3:6].cuda().contiguous(), rays[:, 6].cuda().contiguous()).cpu().numpy().copy()
     np.testing.assert_array_equal(a, b)
+
+
+def test_feistel_sampler_oracle_properties():
+    """The device sampler's permutation (restated in numpy): k distinct in-range values, a full permutation at k = n."""
+    for n, k in [(30000, 2600), (7, 7), (1, 1), (180000, 3000), (1200, 85), (4097, 4097)]:
+        a = okf.feistel_sample(n, k, 4242 + n)
+        assert len(set(a.tolist())) == k and a.min() >= 0 and a.max() < n
+    assert sorted(okf.feistel_sample(3000, 3000, 1).tolist()) == list(range(3000))
+    assert not np.array_equal(okf.feistel_sample(30000, 64, 1), okf.feistel_sample(30000, 64, 2))
+
+
+@pytest.mark.gpu
+def test_gpu_feistel_sampler_and_fused_sampling_bit_exact():
+    import mipsfusion_b200 as mf
+    dev = torch.device("cuda")
+    for n, k, seed in [(30000, 2600, 5), (7, 7, 0), (1, 1, 9), (180000, 3000, 2 ** 31 + 5), (1200, 85, 77)]:
+        got = mf.sample_without_replacement(n, k, dev, seed=seed).cpu().numpy()
+        np.testing.assert_array_equal(got, okf.feistel_sample(n, k, seed & 0xffffffff))
+    fx = np.load(GOLD)
+    cfg = {"sampling": {"kf_n_rays_h": int(fx["nh"]), "kf_n_rays_w": int(fx["nw"])}}
+    st = mf.KeyframeRayStore(cfg, int(fx["H"]), int(fx["W"]), fx["store"].shape[0], "cuda")
+    st.rays.copy_(torch.from_numpy(fx["store"])); st.frame_ids = list(range(fx["store"].shape[0]))
+    store = torch.from_numpy(fx["store"])
+    for first, related, pix in [(2, [2], 20), (1, [1, 4], 30), (0, [0, 2, 3, 5], 37), (1, [1, 0, 2, 3, 4, 5], 40)]:
+        rays, kf_ids, kf_indices, draws = st.sample_rays_in_submap(first, related, pix, seed=100 + pix, return_draws=True)
+        nf, no, nl = st.split_counts(pix, len(related))
+        nr = st.num_rays_to_save
+        n_other_kf = len(related) - 2 if len(related) > 2 else len(related) - 1
+        exp = dict(idx_first=torch.from_numpy(okf.feistel_sample(nr, nf, 100 + pix)))
+        if no:
+            exp["idx_other"] = torch.from_numpy(okf.feistel_sample(n_other_kf * nr, no, 101 + pix))
+        if nl:
+            exp["idx_last"] = torch.from_numpy(okf.feistel_sample(nr, nl, 102 + pix))
+        e_rays, e_ids, e_idx = okf.sample_rays_in_submap(store, first, torch.tensor(related), pix, **exp)
+        np.testing.assert_array_equal(draws.cpu().numpy(), torch.cat([exp["idx_first"], exp.get("idx_other", torch.empty(0, dtype=torch.int64)),
+                                                                       exp.get("idx_last", torch.empty(0, dtype=torch.int64))]).numpy())
+        np.testing.assert_array_equal(rays.cpu().numpy(), e_rays.numpy())
+        np.testing.assert_array_equal(kf_ids.cpu().numpy(), e_ids.numpy())
+        np.testing.assert_array_equal(kf_indices.cpu().numpy(), e_idx.numpy())
