@@ -171,10 +171,11 @@ __global__ void __launch_bounds__(2 * T3_GT, 1) field_fwd_tc3_kernel(FieldDev f,
             }
             T3_MARK(42);
             // ---- grid features: levels [8h, 8h+8) ----
-#pragma unroll
+            // (rolled loops: the two roles run different code at the same time, so instruction-cache footprint matters)
+#pragma unroll 1
             for (int sg = 0; sg < 2; ++sg) {
                 float gf[8];
-#pragma unroll
+#pragma unroll 2
                 for (int ll = 0; ll < 4; ++ll) {
                     float2 v2 = make_float2(0.f, 0.f);
                     if (valid) v2 = grid_level_fwd(x, grid2, level_info(f, 8 * h + 4 * sg + ll), nullptr);

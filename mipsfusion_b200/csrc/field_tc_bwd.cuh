@@ -92,7 +92,10 @@ __device__ __forceinline__ void tb_issue_fwd(const TbCtx& c, const uint8_t* w_hi
     constexpr uint32_t idesc = umma::idesc_bf16(128, 128, 0, 0);
     const uint32_t wh = umma::smem_u32(w_hi), wl = umma::smem_u32(w_lo);
     uint32_t acc = 0;
+    // (rolled: one thread issues, and the kernel's instruction footprint is what the instruction cache has to hold)
+#pragma unroll 1
     for (int pass = 0; pass < 3; ++pass)
+#pragma unroll 1
         for (int ks = 0; ks < KS; ++ks) {
             const uint32_t wb = (pass == 1 ? wl : wh) + (uint32_t)((ks >> 2) * IMG_BLOCK + (ks & 3) * 32);
             umma::mma_ts(c.tmem_base + TB_D, c.tmem_base + (uint32_t)a_col(ks, pass == 2), umma::smem_desc_sw128(wb, 16, 1024), idesc, acc);
@@ -105,7 +108,9 @@ __device__ __forceinline__ void tb_issue_dgrad(const TbCtx& c, const uint8_t* w_
     const uint32_t idesc = umma::idesc_bf16(128, n_out, 0, 1);
     const uint32_t wh = umma::smem_u32(w_hi), wl = umma::smem_u32(w_lo);
     uint32_t acc = 0;
+#pragma unroll 1
     for (int pass = 0; pass < 3; ++pass)
+#pragma unroll 1
         for (int ks = 0; ks < 8; ++ks) {
             const uint32_t a = c.tmem_base + (uint32_t)((pass == 2 ? TB_OP2_LO : TB_OP2_HI) + 8 * ks);
             const uint32_t wb = (pass == 1 ? wl : wh) + (uint32_t)(ks * 2048);
@@ -119,7 +124,9 @@ __device__ __forceinline__ void tb_issue_wgrad(const TbCtx& c, int n_out, bool f
     const uint32_t idesc = umma::idesc_bf16(128, n_out, 1, 1);
     const uint8_t *z_hi = c.r1, *z_lo = c.r1 + 2 * HALF_BLK, *x_hi = c.r2, *x_lo = c.r2 + 2 * HALF_BLK;
     uint32_t acc = first ? 0u : 1u;
+#pragma unroll 1
     for (int pass = 0; pass < 3; ++pass)
+#pragma unroll 1
         for (int ks = 0; ks < 4; ++ks) {
             umma::mma_ss(c.tmem_base + TB_D, umma::desc_mn(pass == 1 ? z_lo : z_hi, 16 * ks, HALF_BLK),
                          umma::desc_mn(pass == 2 ? x_lo : x_hi, 16 * ks, HALF_BLK), idesc, acc);
@@ -466,10 +473,14 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
             umma::tmem_ld8(c.lane_base + TB_D + 64 + 8 * q, r);
             umma::wait_ld();
             if (valid) {
-#pragma unroll
-                for (int ll = 0; ll < 4; ++ll)
-                    grid_level_bwd<WANT_DX>(x, make_float2(__uint_as_float(r[2 * ll]), __uint_as_float(r[2 * ll + 1])), grid2, grad_grid,
-                                            level_info(f, q * 4 + ll), dx);
+#pragma unroll 1
+                for (int ll = 0; ll < 4; ++ll) {
+                    const float2 dy = ll == 0 ? make_float2(__uint_as_float(r[0]), __uint_as_float(r[1]))
+                                    : ll == 1 ? make_float2(__uint_as_float(r[2]), __uint_as_float(r[3]))
+                                    : ll == 2 ? make_float2(__uint_as_float(r[4]), __uint_as_float(r[5]))
+                                              : make_float2(__uint_as_float(r[6]), __uint_as_float(r[7]));
+                    grid_level_bwd<WANT_DX>(x, dy, grid2, grad_grid, level_info(f, q * 4 + ll), dx);
+                }
             }
         }
         TB_MARK(7);
