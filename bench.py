@@ -293,8 +293,8 @@ def run_gpu(args):
     roof = {"bound": "hbm", "kernel": "field_bwd_tc_kernel (tcgen05 recompute-forward + dgrad + wgrad + grid scatter)",
             "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, ncu --set full
-            # (profiles/r1_final_summary.md): 92.45 MB + 25.51 MB; below the algorithmic bytes because the table is L2 resident
-            "traffic": 117.96e6, "traffic_unit": "bytes/launch",
+            # (profiles/r1_final_summary.md): 92.35 MB + 25.06 MB; below the algorithmic bytes because the table is L2 resident
+            "traffic": 117.41e6, "traffic_unit": "bytes/launch",
             "peak_source": which, "ms_per_launch": bwd_ms, "alg_bytes_per_launch": alg_bytes,
             "points_per_launch": P, "active_points_per_launch": n_active,
             "note": "achieved counts 2,048 B for the ACTIVE points only (+ 40 B of d_raw for every point); with SURVEY 8d's "

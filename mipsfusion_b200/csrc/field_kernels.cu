@@ -497,6 +497,7 @@ static inline int64_t act_blocks(int64_t N) { return (N + ACT_BLK - 1) / ACT_BLK
 static inline int64_t act_scratch_words(int64_t N) { return N + act_blocks(N) * 33 + 4; }
 
 static int compact_active_points(const float* d_raw, int64_t N, float* scratch, ActiveMap* am, cudaStream_t st) {
+    if ((uintptr_t)d_raw & 7) { mf_set_error("backward: the upstream gradient must be 8-byte aligned"); return MF_ERR_INVALID; }
     if (N >= (int64_t)1 << 31) { mf_set_error("backward: more than 2^31 points"); return MF_ERR_INVALID; }
     const int64_t nb = act_blocks(N);
     int* idx = reinterpret_cast<int*>(scratch);

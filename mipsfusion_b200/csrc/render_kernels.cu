@@ -330,11 +330,13 @@ __global__ void __launch_bounds__(256) render_loss_bwd_kernel(
             }
         }
         const float w = q.wt[t] * inv;
+        float orgb[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) o[k] = G_rgb[k] * w * sg[t][k] * (1.0f - sg[t][k]);
-        o[3] = dsdf; o[4] = 0.f;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) o[5 + k] = dp[k];
+        for (int k = 0; k < 3; ++k) orgb[k] = G_rgb[k] * w * sg[t][k] * (1.0f - sg[t][k]);
+        // rows are 40 bytes: five 8-byte stores instead of ten 4-byte ones
+        float2* o2 = reinterpret_cast<float2*>(o);
+        o2[0] = make_float2(orgb[0], orgb[1]); o2[1] = make_float2(orgb[2], dsdf); o2[2] = make_float2(0.f, dp[0]);
+        o2[3] = make_float2(dp[1], dp[2]); o2[4] = make_float2(dp[3], dp[4]);
     }
 }
 
@@ -425,6 +427,7 @@ MF_API int mf_render_loss_bwd(const float* raw, const float* z, const float* tar
                               const float* g_rgb, const float* g_depth, float* d_raw, int64_t R, int S, void* stream) {
     (void)counts;
     MF_CHECK_ARG(cfg && raw && z && d_raw && R >= 0);
+    MF_CHECK_ARG(((uintptr_t)d_raw & 7) == 0);                 // 8-byte stores
     MF_CHECK_ARG(S > 0 && S <= MAX_S);
     if (R == 0) return MF_OK;
     MF_CHECK_ARG(!target_d || losses);
