@@ -29,14 +29,14 @@ struct T2Ctx {
 
 __device__ __forceinline__ void t2_group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(T2_GT) : "memory"); }
 
-template <class ColFn>
+template <int N_OUT = 128, class ColFn>
 __device__ __forceinline__ void t2_run_layer(T2Ctx& c, int img_hi, int img_lo, int KS, ColFn a_col) {
     umma::wait_st();
     umma::fence_before_sync();
     t2_group_sync(c.g);
     if (c.tid == 0) {
         umma::fence_after_sync();
-        constexpr uint32_t idesc = umma::idesc_bf16(128, 128, 0, 0);
+        constexpr uint32_t idesc = umma::idesc_bf16(128, N_OUT, 0, 0);     // N_OUT < 128: only the first N_OUT output features
         const uint32_t w_hi = umma::smem_u32(c.img + img_hi), w_lo = umma::smem_u32(c.img + img_lo);
         uint32_t acc = 0;
 #pragma unroll 1
@@ -184,7 +184,21 @@ __global__ void __launch_bounds__(2 * T2_GT, 1) field_fwd_tc2_kernel(FieldDev f,
             }
             t2_store32(c, f0, v);
         }
-        // ---- pts_linear.2 ----
+        // ---- pts_linear.2 (SDF only: just the 64 sdf_emb outputs, 32 per thread) ----
+        if (SDF_ONLY) {
+            t2_run_layer<64>(c, IMG_W2_HI, IMG_W2_LO, 8, [](int ks, bool lo) { return (lo ? T2_A_LO : T2_A_HI) + 8 * ks; });
+            const int f0 = 32 * h;
+            t2_load32(c, T2_D + f0, v);
+            const float4* b4 = reinterpret_cast<const float4*>(c.fw + F_B2 + f0);
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+                const float4 b = b4[k4];
+                v[4 * k4] += b.x; v[4 * k4 + 1] += b.y; v[4 * k4 + 2] += b.z; v[4 * k4 + 3] += b.w;
+            }
+            t2_store32(c, f0, v);
+            umma::tmem_st8(c.lane_base + T2_A_HI + 32 + 8 * h, ghi);
+            umma::tmem_st8(c.lane_base + T2_A_LO + 32 + 8 * h, glo);
+        } else {
         t2_run_layer(c, IMG_W2_HI, IMG_W2_LO, 8, [](int ks, bool lo) { return (lo ? T2_A_LO : T2_A_HI) + 8 * ks; });
         {
             float r[3] = {0.f, 0.f, 0.f};
@@ -222,6 +236,7 @@ __global__ void __launch_bounds__(2 * T2_GT, 1) field_fwd_tc2_kernel(FieldDev f,
             // grid features -> features [64, 96) of the layer-3 operand (operand columns 32 + 8h ..)
             umma::tmem_st8(c.lane_base + T2_A_HI + 32 + 8 * h, ghi);
             umma::tmem_st8(c.lane_base + T2_A_LO + 32 + 8 * h, glo);
+        }
         }
         // ---- sdf_linear.0 + ReLU, logits ----
         t2_run_layer(c, IMG_W3_HI, IMG_W3_LO, 6, [](int ks, bool lo) { return (lo ? T2_A_LO : T2_A_HI) + 8 * ks; });

@@ -41,14 +41,14 @@ struct T3Cons {
 };
 
 // one decoder layer on the consumer side; a_col(ks, lo) = tensor-memory column (relative to the allocation) of k-step ks
-template <class ColFn, class AfterFn>
+template <int N_OUT = 128, class ColFn, class AfterFn>
 __device__ __forceinline__ void t3_run_layer(T3Cons& c, int img_hi, int img_lo, int KS, ColFn a_col, AfterFn after_issue) {
     umma::wait_st();
     umma::fence_before_sync();
     t3_cons_sync();
     if (c.tid == 0) {
         umma::fence_after_sync();
-        constexpr uint32_t idesc = umma::idesc_bf16(128, 128, 0, 0);
+        constexpr uint32_t idesc = umma::idesc_bf16(128, N_OUT, 0, 0);     // N_OUT < 128: only the first N_OUT output features
         const uint32_t w_hi = umma::smem_u32(c.img + img_hi), w_lo = umma::smem_u32(c.img + img_lo);
         uint32_t acc = 0;
 #pragma unroll 1
@@ -235,7 +235,20 @@ __global__ void __launch_bounds__(2 * T3_GT, 1) field_fwd_tc3_kernel(FieldDev f,
                 t3_store32(c, f0, v);
             }
             T3_MARK(51);
-            // ---- pts_linear.2 ----
+            // ---- pts_linear.2 (SDF only: just the 64 sdf_emb outputs, 32 per thread) ----
+            if (SDF_ONLY) {
+                t3_run_layer<64>(c, IMG_W2_HI, IMG_W2_LO, 8, [](int ks, bool lo) { return (lo ? T3_A_LO : T3_A_HI) + 8 * ks; }, []() {});
+                T3_MARK(52);
+                const int f0 = 32 * h;
+                t3_load32(c, T3_D + f0, v);
+                const float4* b4 = reinterpret_cast<const float4*>(c.fw + F_B2 + f0);
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const float4 b = b4[k4];
+                    v[4 * k4] += b.x; v[4 * k4 + 1] += b.y; v[4 * k4 + 2] += b.z; v[4 * k4 + 3] += b.w;
+                }
+                t3_store32(c, f0, v);
+            } else {
             t3_run_layer(c, IMG_W2_HI, IMG_W2_LO, 8, [](int ks, bool lo) { return (lo ? T3_A_LO : T3_A_HI) + 8 * ks; }, []() {});
             T3_MARK(52);
             {
@@ -252,7 +265,7 @@ __global__ void __launch_bounds__(2 * T3_GT, 1) field_fwd_tc3_kernel(FieldDev f,
                     }
                     if (h == 0) {
                         t3_store32(c, f0, v);                    // sdf_emb -> features [0,64) of the layer-3 operand
-                    } else if (!SDF_ONLY) {
+                    } else {
 #pragma unroll
                         for (int ch = 0; ch < 3; ++ch) {
                             const float4* w4 = reinterpret_cast<const float4*>(c.fw + F_WR_EMB + ch * 64 + 32 * half);
@@ -265,10 +278,11 @@ __global__ void __launch_bounds__(2 * T3_GT, 1) field_fwd_tc3_kernel(FieldDev f,
                         }
                     }
                 }
-                if (h == 1 && !SDF_ONLY) {
+                if (h == 1) {
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) c.part[ch * TC_LD + p] = r[ch];
                 }
+            }
             }
             T3_MARK(53);
             // ---- sdf_linear.0 + ReLU (k-steps 0-3: sdf_emb, 4-5: staged grid features); releases the stage ----
