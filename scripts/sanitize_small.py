@@ -32,3 +32,24 @@ jq = mf.JointSubmapQuery([model, model], [torch.eye(4), torch.eye(4)], [np.array
 axes = mf.get_grid_uniform(np.array([-0.5, 0.6, -1.0]), np.array([2.0, 5.0, 2.0]), voxel_size=0.25)
 print(jq.query(axes=axes)["sdf"].shape, L.lib().mf_tc_check_error())
 torch.cuda.synchronize()
+# fused mapper (device batch, host batch, store-fed), keyframe store, device draws, colour joint query, all forward kernels
+from mipsfusion_b200.mapper import FusedMapper
+model.train()
+m = FusedMapper(model)
+args4 = [t.cuda().contiguous() for t in (ro_, rd_, rgb, d)]
+m.step(*args4)
+rays7, pidx, poses, _ = H.synth_batch_packed(200, seed=1)
+print(m.step_host(rays7.pin_memory(), pidx.pin_memory(), poses.cuda()))
+scfg = {"sampling": {"kf_n_rays_h": 6, "kf_n_rays_w": 8}}
+st = mf.KeyframeRayStore(scfg, 60, 80, 4, "cuda")
+for k in range(3):
+    st.add_keyframe({"direction": dirs, "rgb": torch.rand(60, 80, 3, generator=g), "depth": dep.cpu() * 3, "frame_id": k})
+print(m.step_from_store(st, 0, [0, 1, 2], torch.eye(4)[None].repeat(3, 1, 1).cuda(), 40, cur_rays7=st.rays[2, :8].clone()))
+print(mf.sample_without_replacement(1000, 10, torch.device("cuda")).shape, st.sample_rays_in_given_kf([2, 0], 9)[0].shape)
+model.eval()
+print(jq.query(points=torch.rand(500, 3).numpy() * np.array([2.5, 4.4, 3.0]) + np.array([-0.5, 0.6, -1.0]), color=True)["rgb"].shape)
+for impl in (2, 3, 1, 0):
+    L.call("mf_set_decoder_impl", impl)
+    model.run_network(torch.rand(700, 3).cuda()); model.query_sdf(torch.rand(700, 3).cuda())
+torch.cuda.synchronize()
+print("tc error flag", L.lib().mf_tc_check_error())
