@@ -20,10 +20,7 @@ constexpr int BS_R2 = 163840;                          // 32 KB: wgrad X tiles (
 constexpr int BS_F32 = 196608;                         // fp32 section of the image
 constexpr int BS_PART = BS_F32 + ((F_COUNT * 4 + 127) / 128) * 128;
 constexpr int BS_PART_ROWS = 32;                       // 20 logit partial rows + 12 dx partial rows
-constexpr int BS_SACC = BS_PART + BS_PART_ROWS * TC_LD * 4;   // fp32 accumulators of the narrow heads and biases
-constexpr int SA_W4 = 0, SA_WR = 640, SA_B1 = 640 + 345, SA_B2 = SA_B1 + 128, SA_BS1 = SA_B2 + 128, SA_B4 = SA_BS1 + 128, SA_BR = SA_B4 + 5;
-constexpr int SA_COUNT = SA_BR + 3;
-constexpr int BS_BAR = BS_SACC + ((SA_COUNT * 4 + 127) / 128) * 128;
+constexpr int BS_BAR = BS_PART + BS_PART_ROWS * TC_LD * 4;
 constexpr int BS_BYTES = BS_BAR + 32;
 constexpr size_t SMEM_TC_BWD = BS_BYTES + 1024;
 static_assert(SMEM_TC_BWD <= 227 * 1024, "shared memory budget");
@@ -37,7 +34,7 @@ constexpr int TB_G_HI = TB_OP2_HI + 32, TB_G_LO = TB_OP2_LO + 32;   // grid feat
 
 struct TbCtx {
     uint8_t *w2, *w3, *r1, *r2;
-    const float* fw; float* part; float* sacc; uint64_t* bar; uint32_t* tmem_ptr;
+    const float* fw; float* part; uint64_t* bar; uint32_t* tmem_ptr;
     uint32_t tmem_base, lane_base, phase;
     bool ok;
 };
@@ -50,8 +47,7 @@ __device__ __forceinline__ void tb_copy(uint8_t* dst, const uint8_t* __restrict_
 __device__ __forceinline__ void tb_setup(TbCtx& c, uint8_t* smem_raw, const uint8_t* __restrict__ img) {
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     c.w2 = base + BS_W2; c.w3 = base + BS_W3; c.r1 = base + BS_R1; c.r2 = base + BS_R2;
-    c.fw = (const float*)(base + BS_F32); c.part = (float*)(base + BS_PART); c.sacc = (float*)(base + BS_SACC);
-    for (int i = threadIdx.x; i < SA_COUNT; i += blockDim.x) c.sacc[i] = 0.f;
+    c.fw = (const float*)(base + BS_F32); c.part = (float*)(base + BS_PART);
     c.bar = (uint64_t*)(base + BS_BAR); c.tmem_ptr = (uint32_t*)(base + BS_BAR + 8);
     tb_copy(c.w2, img + IMG_W2_HI, 4 * IMG_BLOCK);
     tb_copy(c.w3, img + IMG_W3_HI, 4 * IMG_BLOCK);
@@ -296,7 +292,7 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
                 for (int s = 0; s < 16; ++s) t[s] = g[ch] * e[s];
                 const float r = rs16(t, lane);
                 const int ei = tc_e_slot_to_index(16 * q + (lane & 15));
-                if (lane < 16 && ei >= 0) atomicAdd(&c.sacc[SA_WR + ch * D_RGB_IN + 64 + ei], r);
+                if (lane < 16 && ei >= 0) atomicAdd(&gpart[OFF_WR + ch * D_RGB_IN + 64 + ei], r);
             }
         }
         {
@@ -356,7 +352,7 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
                 float t[32];
 #pragma unroll
                 for (int k = 0; k < 32; ++k) t[k] = g[ch] * v[k];
-                atomicAdd(&c.sacc[SA_WR + ch * D_RGB_IN + 32 * (q - 2) + lane], rs32(t, lane));
+                atomicAdd(&gpart[OFF_WR + ch * D_RGB_IN + 32 * (q - 2) + lane], rs32(t, lane));
             }
         }
         TB_MARK(3);
@@ -424,12 +420,12 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
             float t[32];
 #pragma unroll
             for (int k = 0; k < 32; ++k) t[k] = dz4[ch] * v[k];
-            atomicAdd(&c.sacc[SA_W4 + ch * D_H + 32 * q + lane], rs32(t, lane));
-            if (q == 0) { const float b = warp_sum(dz4[ch]); if (lane == 0) atomicAdd(&c.sacc[SA_B4 + ch], b); }
+            atomicAdd(&gpart[OFF_WS2 + ch * D_H + 32 * q + lane], rs32(t, lane));
+            if (q == 0) { const float b = warp_sum(dz4[ch]); if (lane == 0) atomicAdd(&gpart[OFF_BS2 + ch], b); }
         }
         if (q == 0) {
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) { const float b = warp_sum(g[ch]); if (lane == 0) atomicAdd(&c.sacc[SA_BR + ch], b); }
+            for (int ch = 0; ch < 3; ++ch) { const float b = warp_sum(g[ch]); if (lane == 0) atomicAdd(&gpart[OFF_BR + ch], b); }
         }
         // dZ3 = (Ws2^T dz4) * relu'(h3)
         {
@@ -452,7 +448,7 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
         { float t[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) t[k] = v[k];
-          atomicAdd(&c.sacc[SA_BS1 + 32 * q + lane], rs32(t, lane)); }
+          atomicAdd(&gpart[OFF_BS1 + 32 * q + lane], rs32(t, lane)); }
         TB_MARK(5);
         // ---- layer 3: wgrad (X = [sdf_emb (operand 2), grid features]), then dgrad ----
         tb_wgrad_layer(c, p, q, v,
@@ -495,7 +491,7 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
         { float t[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) t[k] = v[k];
-          atomicAdd(&c.sacc[SA_B2 + 32 * q + lane], rs32(t, lane)); }
+          atomicAdd(&gpart[OFF_B2 + 32 * q + lane], rs32(t, lane)); }
         TB_MARK(8);
         // ---- layer 2: wgrad (X = H1 from operand 1), then dgrad ----
         tb_wgrad_layer(c, p, q, v,
@@ -514,7 +510,7 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
         { float t[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) t[k] = v[k];
-          atomicAdd(&c.sacc[SA_B1 + 32 * q + lane], rs32(t, lane)); }
+          atomicAdd(&gpart[OFF_B1 + 32 * q + lane], rs32(t, lane)); }
         TB_MARK(10);
         // ---- layer 1: wgrad (X = e, 64 slots: this thread owns slots [16q, 16q+16), recomputed here) ----
         {
@@ -600,19 +596,6 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
         __syncthreads();           // accumulator / operand reads of this tile are done before the next tile reuses them
     }
 
-    // ---- flush the narrow-head and bias accumulators into this CTA's partial ----
-    __syncthreads();
-    for (int j = tid; j < SA_COUNT; j += TC_NT) {
-        int dst;
-        if (j < SA_WR) dst = OFF_WS2 + j;
-        else if (j < SA_B1) dst = OFF_WR + (j - SA_WR);
-        else if (j < SA_B2) dst = OFF_B1 + (j - SA_B1);
-        else if (j < SA_BS1) dst = OFF_B2 + (j - SA_B2);
-        else if (j < SA_B4) dst = OFF_BS1 + (j - SA_BS1);
-        else if (j < SA_BR) dst = OFF_BS2 + (j - SA_B4);
-        else dst = OFF_BR + (j - SA_BR);
-        gpart[dst] += c.sacc[j];
-    }
     if (!c.ok && err) atomicExch(err, 1);
     umma::fence_before_sync();
     __syncthreads();
