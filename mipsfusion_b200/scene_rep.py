@@ -31,9 +31,10 @@ class _FieldQueryFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pts, normalize, model, grid, *mlp_params):
-        # gradients w.r.t. the points (pose path) amplify forward rounding, so that route uses the fp32 decoder
+        # gradients w.r.t. the points (pose path) amplify the rounding of the backward's recomputation, so the BACKWARD of
+        # that route uses the fp32 decoder; the forward stays on the tensor cores (see _RenderFn)
         ctx.impl = 1 if pts.requires_grad else 0
-        field = model._field(impl=ctx.impl)
+        field = model._field(impl=0 if (ctx.impl == 1 and getattr(model, "pose_route_tc_forward", True)) else ctx.impl)
         N = pts.shape[0]
         out = torch.empty(N, L.MF_RAW_DIM, device=pts.device, dtype=torch.float32)
         L.call("mf_field_query", L.ptr(pts), C.byref(field), int(normalize), L.ptr(out), N, L.stream())
@@ -101,7 +102,10 @@ class _RenderFn(torch.autograd.Function):
         # pose gradients (d loss / d rays) are ill-conditioned w.r.t. forward rounding (loss residuals cancel, the
         # frequency encoding multiplies by up to 2^7 pi): that route runs the fp32 decoder end to end
         ctx.impl = 1 if (rays_o.requires_grad or rays_d.requires_grad) else 0
-        field = model._field(impl=ctx.impl)
+        # ... its FORWARD can still use the tensor cores: measured pose gradients are as close to the oracle with the
+        # tcgen05 forward (5e-7 .. 1e-6) as with the fp32 one -- the sensitivity is in the backward's recomputation
+        fwd_impl = 0 if (ctx.impl == 1 and getattr(model, "pose_route_tc_forward", True)) else ctx.impl
+        field = model._field(impl=fwd_impl)
         st = L.stream()
         z = torch.empty(R, S, device=dev, dtype=torch.float32)
         counts = torch.empty(2, device=dev, dtype=torch.int64)
@@ -110,7 +114,7 @@ class _RenderFn(torch.autograd.Function):
         raw = torch.empty(R, S, L.MF_RAW_DIM, device=dev, dtype=torch.float32)
         # encoded-feature cache for the backward (tensor-core route, only when a backward can follow)
         feat = None
-        if ctx.impl == 0 and any(ctx.needs_input_grad):       # (grad mode is off inside Function.forward; this is the signal)
+        if ctx.impl == 0 and fwd_impl == 0 and any(ctx.needs_input_grad):       # (grad mode is off inside Function.forward; this is the signal)
             feat = torch.empty(int(L.lib().mf_feat_cache_size(R * S)), device=dev, dtype=torch.uint8)
         ctx.feat = feat
         L.call("mf_field_query_rays", L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), C.byref(field), L.ptr(raw), L.ptr(feat), R, S, st)
