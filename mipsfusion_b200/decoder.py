@@ -23,7 +23,8 @@ class _Workspace:
             n = int(L.lib().mf_field_bwd_workspace_size(int(field_points), int(bool(want_ray_grads))))
         else:
             n = int(L.lib().mf_mlp_grad_workspace_size()) + int(extra_floats)
-        key = (device.type, device.index)
+        # one buffer per (device, stream): backward passes issued on different streams must not share scratch
+        key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0)
         buf = cls._bufs.get(key)
         if buf is None or buf.numel() < n:
             buf = torch.empty(n, device=device, dtype=torch.float32)

@@ -18,6 +18,25 @@ def test_header_and_prototypes_agree():
     assert header_functions() == sorted(L.PROTOTYPES.keys())
 
 
+def header_signatures():
+    """name -> number of parameters, parsed from the declarations in the header."""
+    src = open(L.HEADER_PATH).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(mf_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def test_prototype_arity_matches_header():
+    """Every ctypes prototype has as many arguments as the C declaration it binds (guards against signature drift)."""
+    sig = header_signatures()
+    assert sorted(sig) == sorted(L.PROTOTYPES.keys())
+    for name, (_, argtypes) in L.PROTOTYPES.items():
+        assert len(argtypes) == sig[name], (name, len(argtypes), sig[name])
+
+
 def test_library_loads_and_exports_every_symbol():
     if not os.path.exists(L.LIB_PATH):
         import __graft_entry__ as g
