@@ -194,6 +194,12 @@ int mf_adam_step(float* p, float* g, float* m, float* v, int64_t n, double lr, d
 int mf_adam_step_sharded(const uint64_t* peer_bases, int world, int rank, int64_t off_p, int64_t off_g, int64_t off_g_clear,
                          float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
                          double weight_decay, int step, uint64_t multicast_base, void* stream);
+/* The two Adam groups of a mapping step (mipsfusion.py:580-584: hash grid and decoder, each with its own lr / eps / weight
+ * decay) in one launch, gradients cleared.  n0, n1 multiples of 4, 16-byte aligned arrays (pad the decoder blob with zeros:
+ * a zero parameter with a zero gradient stays zero). */
+int mf_adam_step_pair(float* p0, float* g0, float* m0, float* v0, int64_t n0, double lr0, double eps0, double wd0,
+                      float* p1, float* g1, float* m1, float* v1, int64_t n1, double lr1, double eps1, double wd1,
+                      double beta1, double beta2, int step, void* stream);
 /* The same update for a parameter group of n_tensors tensors (host arrays of device pointers and sizes). */
 int mf_adam_step_multi(int n_tensors, float* const* p_host, float* const* g_host, float* const* m_host,
                        float* const* v_host, const int64_t* n_host, double lr, double beta1, double beta2, double eps,

@@ -8,8 +8,7 @@
 // ---------------------------------------------------------------------------------------------
 // Weight re-layout (runs once per optimiser step; 36.6 k floats).
 // ---------------------------------------------------------------------------------------------
-__global__ void mlp_prepare_kernel(const float* __restrict__ mlp, float* __restrict__ prep) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void mlp_prepare_simt(const float* __restrict__ mlp, float* __restrict__ prep, int i) {
     if (i >= PREP_SIMT_SIZE) return;
     float v = 0.f;
     if (i < MF_MLP_PARAMS) {
@@ -38,8 +37,7 @@ __global__ void mlp_prepare_kernel(const float* __restrict__ mlp, float* __restr
 }
 
 // bf16 hi/lo, 128B-swizzled K-major weight image + fp32 head section for the tcgen05 decoder (field_tc.cuh)
-__global__ void mlp_prepare_tc_kernel(const float* __restrict__ mlp, uint8_t* __restrict__ img) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void mlp_prepare_tc(const float* __restrict__ mlp, uint8_t* __restrict__ img, int t) {
     // one thread per (layer, n, k) weight element: 128 x (64 + 128 + 128)
     if (t < 128 * 320) {
         const int n = t / 320, kk = t % 320;
@@ -76,6 +74,14 @@ __global__ void mlp_prepare_tc_kernel(const float* __restrict__ mlp, uint8_t* __
         else v = (j - F_BS2) < 5 ? mlp[OFF_BS2 + (j - F_BS2)] : 0.f;
         reinterpret_cast<float*>(img + IMG_F32)[j] = v;
     }
+}
+
+// one launch for both layouts: the first blocks write the fp32 copies, the rest the tensor-core image
+constexpr int PREP_BLOCKS_SIMT = (PREP_SIMT_SIZE + 255) / 256;
+constexpr int PREP_BLOCKS_TC = (128 * 320 + F_COUNT + 255) / 256;
+__global__ void __launch_bounds__(256) mlp_prepare_kernel(const float* __restrict__ mlp, float* __restrict__ prep) {
+    if (blockIdx.x < PREP_BLOCKS_SIMT) mlp_prepare_simt(mlp, prep, blockIdx.x * 256 + threadIdx.x);
+    else mlp_prepare_tc(mlp, reinterpret_cast<uint8_t*>(prep + PREP_TC), (blockIdx.x - PREP_BLOCKS_SIMT) * 256 + threadIdx.x);
 }
 
 // (the generic forward kernel templates live in field_launch.cuh / field_tc_launch.cuh)
@@ -390,10 +396,7 @@ MF_API int64_t mf_mlp_prep_size(void) { return PREP_SIZE; }
 
 MF_API int mf_mlp_prepare(const float* mlp, float* mlp_prep, void* stream) {
     MF_CHECK_ARG(mlp && mlp_prep);
-    mlp_prepare_kernel<<<(PREP_SIMT_SIZE + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mlp, mlp_prep);
-    MF_LAUNCH_CHECK();
-    mlp_prepare_tc_kernel<<<(128 * 320 + F_COUNT + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        mlp, reinterpret_cast<uint8_t*>(mlp_prep + PREP_TC));
+    mlp_prepare_kernel<<<PREP_BLOCKS_SIMT + PREP_BLOCKS_TC, 256, 0, (cudaStream_t)stream>>>(mlp, mlp_prep);
     MF_LAUNCH_CHECK();
     return MF_OK;
 }

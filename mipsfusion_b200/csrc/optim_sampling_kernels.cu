@@ -194,6 +194,48 @@ MF_API int mf_adam_step_sharded(const uint64_t* peer_bases, int world, int rank,
     return MF_OK;
 }
 
+// Two tensors with their own hyper-parameters in ONE launch (the hash grid and the decoder blob of a mapping step): the
+// first b0 blocks stride over tensor 0, the remaining blocks over tensor 1.  Both lengths must be multiples of 4.
+struct AdamTensor { float4 *p, *g, *m, *v; int64_t n4; AdamScalars a; };
+
+__global__ void __launch_bounds__(256) adam_pair_kernel(AdamTensor t0, AdamTensor t1, int b0) {
+    const bool first = (int)blockIdx.x < b0;
+    const AdamTensor& t = first ? t0 : t1;
+    const int64_t nb = first ? b0 : (int)gridDim.x - b0, bi = first ? blockIdx.x : blockIdx.x - b0;
+    for (int64_t i = bi * blockDim.x + threadIdx.x; i < t.n4; i += nb * blockDim.x) {
+        float4 pp = t.p[i], gg = t.g[i], mm = t.m[i], vv = t.v[i];
+        adam_one(pp.x, gg.x, mm.x, vv.x, t.a); adam_one(pp.y, gg.y, mm.y, vv.y, t.a);
+        adam_one(pp.z, gg.z, mm.z, vv.z, t.a); adam_one(pp.w, gg.w, mm.w, vv.w, t.a);
+        t.p[i] = pp; t.m[i] = mm; t.v[i] = vv;
+        t.g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+static AdamScalars adam_scalars(double lr, double beta1, double beta2, double eps, double weight_decay, int step) {
+    AdamScalars a;
+    a.w1 = (float)(1.0 - beta1); a.beta2 = (float)beta2; a.w2 = (float)(1.0 - beta2);
+    a.neg_step = (float)(-(lr / (1.0 - pow(beta1, (double)step))));
+    a.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
+    a.eps = (float)eps; a.wd = (float)weight_decay;
+    return a;
+}
+
+MF_API int mf_adam_step_pair(float* p0, float* g0, float* m0, float* v0, int64_t n0, double lr0, double eps0, double wd0,
+                             float* p1, float* g1, float* m1, float* v1, int64_t n1, double lr1, double eps1, double wd1,
+                             double beta1, double beta2, int step, void* stream) {
+    MF_CHECK_ARG(p0 && g0 && m0 && v0 && p1 && g1 && m1 && v1 && step >= 1);
+    MF_CHECK_ARG(n0 > 0 && n1 > 0 && (n0 & 3) == 0 && (n1 & 3) == 0);
+    MF_CHECK_ARG((((uintptr_t)p0 | (uintptr_t)g0 | (uintptr_t)m0 | (uintptr_t)v0 | (uintptr_t)p1 | (uintptr_t)g1 | (uintptr_t)m1 | (uintptr_t)v1) & 15) == 0);
+    AdamTensor t0{(float4*)p0, (float4*)g0, (float4*)m0, (float4*)v0, n0 / 4, adam_scalars(lr0, beta1, beta2, eps0, wd0, step)};
+    AdamTensor t1{(float4*)p1, (float4*)g1, (float4*)m1, (float4*)v1, n1 / 4, adam_scalars(lr1, beta1, beta2, eps1, wd1, step)};
+    const int64_t cap = (int64_t)mf_sm_count_cached() * 8;
+    const int64_t w0 = (t0.n4 + 255) / 256, w1 = (t1.n4 + 255) / 256;
+    const int b0 = (int)(w0 < cap ? w0 : cap), b1 = (int)(w1 < 64 ? w1 : 64);
+    adam_pair_kernel<<<(unsigned)(b0 + b1), 256, 0, (cudaStream_t)stream>>>(t0, t1, b0);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}
+
 MF_API int mf_adam_step_multi(int n_tensors, float* const* p, float* const* g, float* const* m, float* const* v,
                               const int64_t* n, double lr, double beta1, double beta2, double eps, double weight_decay,
                               int step, int zero_grad, void* stream) {

@@ -32,10 +32,15 @@ class FusedMapper:
         self.loss_w = torch.tensor([t["rgb_weight"], t["depth_weight"], t["sdf_weight"], t["fs_weight"]], dtype=torch.float32,
                                    device=self.dev)
         self.grid = model.embed_fn.params.data
-        self.mlp = model.decoder.flat_weights().contiguous()            # master copy while stepping
+        # master copy of the decoder blob while stepping, zero-padded to a multiple of 4 floats (one vectorised Adam launch)
+        nm = L.MF_MLP_PARAMS
+        self._mlp_pad = torch.zeros((nm + 3) // 4 * 4, device=self.dev, dtype=torch.float32)
+        self._mlp_pad[:nm].copy_(model.decoder.flat_weights())
+        self.mlp = self._mlp_pad[:nm]
         self.prep = torch.empty(int(L.lib().mf_mlp_prep_size()), device=self.dev, dtype=torch.float32)
         self.g_grid = torch.zeros_like(self.grid); self.m_grid = torch.zeros_like(self.grid); self.v_grid = torch.zeros_like(self.grid)
-        self.g_mlp = torch.zeros_like(self.mlp); self.m_mlp = torch.zeros_like(self.mlp); self.v_mlp = torch.zeros_like(self.mlp)
+        self._g_mlp_pad = torch.zeros_like(self._mlp_pad); self.g_mlp = self._g_mlp_pad[:nm]
+        self.m_mlp = torch.zeros_like(self._mlp_pad); self.v_mlp = torch.zeros_like(self._mlp_pad)
         # Data parallel with NVLink peer memory: parameters and (double-buffered) gradients live in a symmetric arena and
         # the gradient all-reduce + Adam + parameter broadcast become one sharded kernel (mf_adam_step_sharded).
         # peer_memory: True (require), False (NCCL all-reduce + replicated Adam), "auto" (try, fall back to NCCL).
@@ -129,7 +134,7 @@ class FusedMapper:
         L.call("mf_field_query_rays_bwd", L.ptr(rays_o), L.ptr(rays_d), L.ptr(b["z"]), C.byref(field), L.ptr(b["d_raw"]),
                L.ptr(b["feat"]), L.ptr(self.g_grid), L.ptr(self.g_mlp), None, None, L.ptr(_Workspace.get(self.dev, field_points=R * S)), R, S, st)
         e4 = ev()
-        self.launches += 7
+        self.launches += 9            # sample_z, field fwd, render+loss fwd (2), render+loss bwd, compaction (2), field bwd, partial reduce
         if update:
             if self.arena is not None:
                 self.apply_gradients_sharded()
@@ -199,12 +204,19 @@ class FusedMapper:
         """Adam on (grid, decoder) with the reference's groups (mipsfusion.py:580-584), zero_grad fused in."""
         self.step_count += 1
         st = L.stream()
-        L.call("mf_adam_step", L.ptr(self.grid), L.ptr(self.g_grid), L.ptr(self.m_grid), L.ptr(self.v_grid), self.grid.numel(),
-               float(self.lr_embed), 0.9, 0.99, 1e-15, 0.0, self.step_count, 1, st)
-        L.call("mf_adam_step", L.ptr(self.mlp), L.ptr(self.g_mlp), L.ptr(self.m_mlp), L.ptr(self.v_mlp), self.mlp.numel(),
-               float(self.lr_decoder), 0.9, 0.99, 1e-8, 1e-6, self.step_count, 1, st)
+        if self.grid.numel() % 4 == 0 and self.grid.data_ptr() % 16 == 0:
+            L.call("mf_adam_step_pair", L.ptr(self.grid), L.ptr(self.g_grid), L.ptr(self.m_grid), L.ptr(self.v_grid), self.grid.numel(),
+                   float(self.lr_embed), 1e-15, 0.0, L.ptr(self._mlp_pad), L.ptr(self._g_mlp_pad), L.ptr(self.m_mlp), L.ptr(self.v_mlp),
+                   self._mlp_pad.numel(), float(self.lr_decoder), 1e-8, 1e-6, 0.9, 0.99, self.step_count, st)
+            self.launches += 1
+        else:
+            L.call("mf_adam_step", L.ptr(self.grid), L.ptr(self.g_grid), L.ptr(self.m_grid), L.ptr(self.v_grid), self.grid.numel(),
+                   float(self.lr_embed), 0.9, 0.99, 1e-15, 0.0, self.step_count, 1, st)
+            L.call("mf_adam_step", L.ptr(self._mlp_pad), L.ptr(self._g_mlp_pad), L.ptr(self.m_mlp), L.ptr(self.v_mlp), self._mlp_pad.numel(),
+                   float(self.lr_decoder), 0.9, 0.99, 1e-8, 1e-6, self.step_count, 1, st)
+            self.launches += 2
         L.call("mf_mlp_prepare", L.ptr(self.mlp), L.ptr(self.prep), st)
-        self.launches += 4
+        self.launches += 1
 
     def apply_gradients_sharded(self):
         """Data-parallel update over peer memory: barrier, one sharded reduce + Adam + broadcast kernel per tensor,
@@ -226,7 +238,7 @@ class FusedMapper:
         a.barrier()                                                  # every slab has reached every replica
         self.g_grid, self.g_mlp = self._g_grid[nxt], self._g_mlp[nxt]
         L.call("mf_mlp_prepare", L.ptr(self.mlp), L.ptr(self.prep), st)
-        self.launches += 4
+        self.launches += 3            # two sharded updates + weight prepare (the barriers are torch's kernels)
 
     def sync_to_module(self):
         """Write the stepped decoder weights back into the module's nn.Parameters (the grid is updated in place)."""
