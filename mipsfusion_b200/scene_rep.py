@@ -221,14 +221,22 @@ class JointEncoding(nn.Module):
         if not grid.is_cuda:
             raise L.MipsFusionB200Error("JointEncoding must live on a CUDA device (no CPU fallback); call .to('cuda')")
         prep = keep[1] if keep is not None else self.decoder.prepared()
-        f = L.Field()
-        f.grid, f.mlp_prep = grid.data_ptr(), prep.data_ptr()
-        a, b = self._norm_host()
-        for k in range(3):
-            f.norm_a[k], f.norm_b[k] = a[k], b[k]
-        f.norm_factor = float(self.config["training"]["norm_factor"])
-        f.decoder_impl = int(impl)
-        f.meta = self.embed_fn.meta
+        # the descriptor only depends on the two device pointers and the decoder selection: reuse it between calls
+        key = (grid.data_ptr(), prep.data_ptr(), int(impl))
+        cache = self.__dict__.setdefault("_field_cache", {})
+        f = cache.get(key)
+        if f is None:
+            if len(cache) > 16:
+                cache.clear()
+            f = L.Field()
+            f.grid, f.mlp_prep = grid.data_ptr(), prep.data_ptr()
+            a, b = self._norm_host()
+            for k in range(3):
+                f.norm_a[k], f.norm_b[k] = a[k], b[k]
+            f.norm_factor = float(self.config["training"]["norm_factor"])
+            f.decoder_impl = int(impl)
+            f.meta = self.embed_fn.meta
+            cache[key] = f
         f._keepalive = (grid, prep)
         return f
 
@@ -255,7 +263,7 @@ class JointEncoding(nn.Module):
 
     def __getstate__(self):
         s = self.__dict__.copy()
-        for k in ("_norm_cache", "_lin_cache"):
+        for k in ("_norm_cache", "_lin_cache", "_field_cache"):
             s.pop(k, None)
         return s
 
