@@ -270,6 +270,9 @@ def run_gpu(args):
     # ---- tracking metric (BASELINE configs[1] shape): RandomOptimizer scoring 1024 candidates x 2048 pixels ----
     also = {"e2e_autograd_api_rays_per_s": e2e_autograd,
             "e2e_autograd_api": "JointEncoding.forward + loss.backward() + FusedAdam.step(), same host batch / loss read-back"}
+    if world > 1:                      # the two other sharded paths, strong scaling on the single-GPU shapes
+        also.update(tracking_bench(model, cfg, dev, group=group))
+        also.update(joint_query_bench(dev, group=group))
     if world == 1:
         also.update(tracking_bench(model, cfg, dev))
         also.update(frame_bench(dev))
@@ -328,8 +331,18 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def tracking_bench(model, cfg, dev, iters=5):
-    """pose candidates/s of RandomOptimizer scoring at the BASELINE tracking shape."""
+def _max_over_ranks(x, dev, group):
+    import torch
+    t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t)
+
+
+def tracking_bench(model, cfg, dev, iters=5, group=None):
+    """pose candidates/s of RandomOptimizer scoring at the BASELINE tracking shape.  With a process group the SAME 1024
+    candidates are sharded across the ranks (strong scaling; one all-gather of 9 floats per candidate per iteration)."""
     import types
     import torch
     import mipsfusion_b200 as mf
@@ -346,7 +359,7 @@ def tracking_bench(model, cfg, dev, iters=5):
     ds = types.SimpleNamespace(H=460, W=620, fx=320.0, fy=320.0, cx=309.5, cy=229.5, rays_d=dirs)
     g = torch.Generator().manual_seed(0)
     particles = torch.randn(Cn, 6, generator=g).clamp(-2, 2); particles[0] = 0
-    ro = mf.RandomOptimizer(tcfg, types.SimpleNamespace(dataset=ds, device=str(dev)), particles=particles)
+    ro = mf.RandomOptimizer(tcfg, types.SimpleNamespace(dataset=ds, device=str(dev)), particles=particles, group=group)
     model.eval()
     target_d = sub["depth"].reshape(-1).to(dev); rays_d = dirs[rows, cols].contiguous().to(dev)
     rot, trans = c2w[:3, :3].contiguous().to(dev), c2w[:3, 3].contiguous().to(dev)
@@ -360,10 +373,11 @@ def tracking_bench(model, cfg, dev, iters=5):
         fit, ms, p7 = ro.score(model, rot, trans, search, target_d, rays_d)
         ro.update(fit, ms, p7, rot.clone(), trans.clone(), search.clone())
     b.record(); torch.cuda.synchronize()
-    ms_it = a.elapsed_time(b) / iters
+    ms_it = _max_over_ranks(a.elapsed_time(b) / iters, dev, group)
     model.train()
     return {"tracking_pose_candidates_per_s": Cn / (ms_it * 1e-3), "tracking_ms_per_ro_iteration": ms_it,
-            "tracking_shape": f"{Cn} candidates x {nr * nc} pixels, SDF-only field query + per-candidate reduction + swarm update"}
+            "tracking_shape": f"{Cn} candidates x {nr * nc} pixels, SDF-only field query + per-candidate reduction + swarm update"
+                              + ("" if group is None else "; the candidates are sharded across the GPUs (strong scaling)")}
 
 
 def emit(obj):
@@ -403,7 +417,7 @@ def store_bench(mapper, dev, steps):
                                "mf_gen_rays_packed -> map step; no host data per step"}
 
 
-def joint_query_bench(dev, res=512, n_submaps=16):
+def joint_query_bench(dev, res=512, n_submaps=16, group=None):
     """BASELINE configs[4] shape: joint SDF grid query at res^3 over n_submaps submaps (Mesher / render_mesh path):
     containment + world->submap transform + field query (sdf, entropy) + entropy/distance-weighted blend."""
     import numpy as np
@@ -426,16 +440,21 @@ def joint_query_bench(dev, res=512, n_submaps=16):
         poses.append(T); amin.append(a); amax.append(b); cents.append(((a + b) / 2).astype(np.float32))
     axes = [np.linspace(lo[k], hi[k], res) for k in range(3)]
     jq = mf.JointSubmapQuery(models, poses, amin, amax, cents)
-    jq.query(axes=[a_[:64] for a_ in axes])                      # warm-up
+    kw = {} if group is None else dict(group=group, shard="points")
+    jq.query(axes=[a_[:64] for a_ in axes], **kw)                # warm-up
     torch.cuda.synchronize()
+    if group is not None:
+        import torch.distributed as dist
+        dist.barrier()
     t0 = time.perf_counter()
-    out = jq.query(axes=axes)
+    out = jq.query(axes=axes, **kw)
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    dt = _max_over_ranks(time.perf_counter() - t0, dev, group)
     frac = float(out["mask"].float().mean())
     del out
     return {"joint_query_grid_points_per_s": res ** 3 / dt, "joint_query_s": dt,
-            "joint_query_shape": f"{res}^3 grid x {n_submaps} submaps (T=2^{HASH} each), {frac:.2f} of the points inside >= 1 submap"}
+            "joint_query_shape": f"{res}^3 grid x {n_submaps} submaps (T=2^{HASH} each), {frac:.2f} of the points inside >= 1 submap"
+                                 + ("" if group is None else "; the grid points are sharded across the GPUs (strong scaling, results stay sharded)")}
 
 
 def frame_bench(dev, frames=3):
