@@ -181,12 +181,12 @@ class FusedMapper:
         -1 = last pose), generate the rays with ``poses_all`` (K,4,4) and run :meth:`step`.  Returns the device losses."""
         n_cur = 0 if cur_rays7 is None else int(cur_rays7.shape[0])
         R = int(pix_num) + n_cur
-        sb = self._bufs.get(("store", R))
+        sb = self._bufs.get(("store", int(pix_num), n_cur))       # (keyed by the split: the tail of `idx` must stay -1)
         if sb is None:
             f32 = dict(device=self.dev, dtype=torch.float32)
             sb = dict(rays7=torch.empty(R, 7, **f32), idx=torch.full((R,), -1, device=self.dev, dtype=torch.int64),
                       o=torch.empty(R, 3, **f32), d=torch.empty(R, 3, **f32), rgb=torch.empty(R, 3, **f32), depth=torch.empty(R, **f32))
-            self._bufs[("store", R)] = sb
+            self._bufs[("store", int(pix_num), n_cur)] = sb
         rays, _, kf_indices = store.sample_rays_in_submap(first_kf_Id, related_kf_ids, pix_num, out=sb["rays7"], **draws)[:3]
         if rays.data_ptr() != sb["rays7"].data_ptr():               # explicit draws: gathered into a fresh tensor
             sb["rays7"][:pix_num].copy_(rays)
