@@ -153,3 +153,17 @@ def test_gpu_feistel_sampler_and_fused_sampling_bit_exact():
         np.testing.assert_array_equal(rays.cpu().numpy(), e_rays.numpy())
         np.testing.assert_array_equal(kf_ids.cpu().numpy(), e_ids.numpy())
         np.testing.assert_array_equal(kf_indices.cpu().numpy(), e_idx.numpy())
+
+
+def test_split_counts_host_logic_matches_oracle_and_reference_formula():
+    """first / other / last ray counts of sample_rays_in_submap (model/keyframeSet.py:392,402,409,413): host mirror == oracle,
+    they add up to the request and follow the reference's max(n // k, n // 10 | n // 5) rule."""
+    from mipsfusion_b200.keyframe_store import KeyframeRayStore
+    for pix in (1, 9, 10, 37, 64, 2048, 2600, 4095):
+        for k in (1, 2, 3, 4, 7, 12, 50):
+            a = KeyframeRayStore.split_counts(pix, k)
+            assert a == okf.split_counts(pix, k)
+            assert sum(a) == pix and min(a) >= 0
+            assert a[0] == max(pix // k, pix // 10)
+            if k > 2:
+                assert a[2] == max(pix // k, pix // 5)
