@@ -31,10 +31,12 @@ class _FieldQueryFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pts, normalize, model, grid, *mlp_params):
-        # gradients w.r.t. the points (pose path) amplify the rounding of the backward's recomputation, so the BACKWARD of
-        # that route uses the fp32 decoder; the forward stays on the tensor cores (see _RenderFn)
+        # gradients w.r.t. the points (pose path): fp32 decoder for the forward AND the backward.  Callers of this route
+        # difference the outputs of two submaps (InactiveMap.get_SDF_dif): the residual is small by design, so the 1e-4 of
+        # the tensor-core forward would be a percent-level error of the pose gradient (measured 3e-2 on
+        # tests/golden/overlap.npz); the ray route (_RenderFn) keeps its tensor-core forward, its residuals are against targets
         ctx.impl = 1 if pts.requires_grad else 0
-        field = model._field(impl=0 if (ctx.impl == 1 and getattr(model, "pose_route_tc_forward", True)) else ctx.impl)
+        field = model._field(impl=ctx.impl)
         N = pts.shape[0]
         out = torch.empty(N, L.MF_RAW_DIM, device=pts.device, dtype=torch.float32)
         L.call("mf_field_query", L.ptr(pts), C.byref(field), int(normalize), L.ptr(out), N, L.stream())

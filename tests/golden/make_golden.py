@@ -214,6 +214,56 @@ def gen_blend():
                         dist_weight=ref_mh.convert_dist_to_weight(dist))
 
 
+def gen_overlap():
+    """InactiveMap.get_SDF_dif / get_SDF_dif2 (the reference's own methods, called unbound on a stub) with two reference
+    JointEncoding models; loss and its gradients w.r.t. the two first-keyframe poses."""
+    import types as _types
+    sys.modules.setdefault("Logger", _types.ModuleType("Logger"))          # Logger.py needs matplotlib; InactiveMap only imports the name
+    if not hasattr(sys.modules["Logger"], "Logger"):
+        sys.modules["Logger"].Logger = object
+    import InactiveMap as ref_im
+    from mipsfusion_b200 import synth
+    cfg = small_config(10)
+    models = []
+    for seed in (21, 22):
+        m = build_ref_model(cfg)
+        g = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            m.embed_fn.params.copy_((torch.rand(m.embed_fn.params.shape, generator=g) * 2 - 1) * 0.5)
+            for p_ in m.decoder.parameters():
+                p_.add_(0.05 * torch.randn(p_.shape, generator=g))
+        m.eval()
+        models.append(m)
+    g = torch.Generator().manual_seed(5)
+    poses = synth.trajectory(6)
+    dirs = synth.camera_rays()
+    frame = synth.render_frame(poses[2], dirs[::19, ::27].contiguous())
+    rays = synth.frame_rays(frame)
+    N = 96
+    rays = rays[torch.randperm(rays.shape[0], generator=g)[:N]].clone()
+    rays[:5, 6] = 0.0
+    kf_idx = torch.randint(0, 3, (N,), generator=g)
+    ovlp = torch.stack([poses[2], poses[3], poses[4]])[kf_idx]                      # (N,4,4) world poses of the overlapping keyframes
+    first1 = poses[0].clone().requires_grad_(True); first2 = poses[1].clone().requires_grad_(True)
+    stub = _types.SimpleNamespace(device="cpu", trunc_value=cfg["training"]["trunc"], model_list=models)
+    stub.infer_pts = lambda *a: ref_im.InactiveMap.infer_pts(stub, *a)
+    loss = ref_im.InactiveMap.get_SDF_dif(stub, rays, ovlp, 0, 1, first1, first2)
+    loss.backward()
+    out = {"rays": rays.numpy(), "ovlp": ovlp.numpy(), "first1": first1.detach().numpy(), "first2": first2.detach().numpy(),
+           "loss": loss.detach().numpy(), "g_first1": first1.grad.numpy().copy(), "g_first2": first2.grad.numpy().copy(),
+           "trunc": np.asarray(cfg["training"]["trunc"]), "hash_size": np.asarray(10)}
+    first1.grad = None; first2.grad = None
+    mask = (torch.rand(N, 1, generator=g) > 0.3)
+    loss2 = ref_im.InactiveMap.get_SDF_dif2(stub, rays[:, 6:7], rays[:, :3], mask, poses[3][None], 1, 0, first1, first2)
+    loss2.backward()
+    out.update(mask2=mask.numpy(), pose2=poses[3][None].numpy(), loss2=loss2.detach().numpy(),
+               g2_first1=first1.grad.numpy().copy(), g2_first2=first2.grad.numpy().copy())
+    for i, m in enumerate(models):
+        for k, v in m.state_dict().items():
+            out[f"w{i}:" + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "overlap.npz"), **out)
+
+
 def gen_keyframes():
     """The reference's own KeyframeSet (ray part) with python random.sample patched to replay recorded draws."""
     import random as pyrandom
@@ -261,6 +311,9 @@ def gen_keyframes():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "keyframes":
         gen_keyframes(); sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "overlap":
+        gen_overlap(); sys.exit(0)
+    gen_overlap()
     gen_keyframes()
     gen_lattice(); gen_sampling(); gen_losses(); gen_decoder()
     cfg, model = gen_scene()
