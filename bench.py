@@ -27,9 +27,18 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 R_RAYS, N_SAMPLES_D, N_RANGE_D, HASH = 4096, 32, 11, 19
 S = N_SAMPLES_D + N_RANGE_D
-ALG_BYTES_PER_POINT_BWD = 2048          # 1,024 B scatter (+ 1,024 B re-gather for the recomputed forward)
-ALG_BYTES_PER_POINT_FWD = 1024
+ALG_BYTES_PER_POINT = 1024              # 16 levels x 8 corners x 2 features x 4 B gathered (forward) / scattered (backward)
 ADAM_BYTES_PER_PARAM = 32
+DTYPE = "f32 (decoder contractions as bf16x3 hi/lo splits on tcgen05, fp32 accumulate; encodings, render, losses, Adam in fp32)"
+
+
+def ncu_traffic():
+    """DRAM bytes per launch from the committed ncu --set full capture (kernel name -> bytes), {} if none is committed."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 def peaks():
@@ -119,7 +128,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_rays = 1024
+    n_rays = R_RAYS                    # the full 4096-ray batch of the GPU arm (about 0.5 s per step on 16 host threads)
     step = cpu_step_fn(n_rays)
     for _ in range(args.warmup):
         step()
@@ -129,7 +138,8 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     val = n_rays * args.steps / dt
     cores = torch.get_num_threads()
-    sample = f"{args.steps} steps x {n_rays} rays x {S} samples (1/{R_RAYS // n_rays} of the 4096-ray batch), full T=2^19 grid + dense Adam"
+    sample = (f"{args.steps} steps x {n_rays} rays x {S} samples (the full batch of the GPU arm), full T=2^19 grid + dense Adam, "
+              f"oracle port of the reference's PyTorch path on the host cores, torch {torch.__version__}")
     emit(({
         "impl": "reference", "metric": "map_step_rays_per_s", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
@@ -216,12 +226,22 @@ def run_gpu(args):
             emit({"metric": "map_step_rays_per_s", "value": value, "ms_per_step": dev_ms / args.steps, "quick": True})
         return
     # ---- per-kernel timing of the dominant kernel (separate pass, events around each launch) ----
+    import ctypes as C
+    from mipsfusion_b200 import _lib as L
     mapper.timing = {}
+    kernel_acc = {"field_fwd": [], "field_bwd": []}
+    L.call("mf_debug_kernel_timer", 1)
     for _ in range(args.steps):
         flush.zero_()
         mapper.step(ro, rd, tc, td)
+        for slot, name in ((0, "field_fwd"), (1, "field_bwd")):
+            ms = C.c_float(0.0)
+            L.call("mf_debug_kernel_ms", slot, C.byref(ms))
+            kernel_acc[name].append(ms.value)
     torch.cuda.synchronize()
+    L.call("mf_debug_kernel_timer", 0)
     phase_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in mapper.timing.items()}
+    kernel_ms = {k: sum(v) / len(v) for k, v in kernel_acc.items()}
     mapper.timing = None
 
     # ---- e2e: public API with HOST buffers; every step copies the pinned host batch H2D and reads the losses back ----
@@ -278,6 +298,8 @@ def run_gpu(args):
         also.update(frame_bench(dev))
         also.update(joint_query_bench(dev))
         also.update(store_bench(mapper, dev, args.steps))
+    also_roof = {k[len("_roof_"):]: also.pop(k) for k in [k for k in also if k.startswith("_roof_")]}
+    also_roof = {k: v for k, v in also_roof.items() if v}
 
     if rank != 0:
         if world > 1:
@@ -286,26 +308,44 @@ def run_gpu(args):
         return
     hbm, tf, which = peaks()
     P = R_RAYS * S
-    bwd_ms = phase_ms.get("field_bwd", float("nan"))
-    # points whose upstream gradient row is non-zero: the only ones the backward has to visit (the kernel skips the rest)
+    n_params = 9014144 + 36577
+    # ---- roofline: algorithmic bytes / launch of the dominant kernel over its own CUDA-event duration ----
+    # field backward: 1,024 B of scatter per point x ALL points of the launch (the kernel only visits the points whose
+    # upstream gradient row is non-zero, the algorithmic count is the work the reference's autograd does); duration = the
+    # event pair the library records around the kernel launch itself (mf_debug_kernel_timer), not the phase around it
+    bwd_ms = kernel_ms.get("field_bwd", float("nan"))
+    fwd_ms = kernel_ms.get("field_fwd", float("nan"))
     d_raw = mapper._bufs[(R_RAYS, S)]["d_raw"]
     n_active = int((d_raw.view(-1, d_raw.shape[-1]) != 0).any(-1).sum())
-    alg_bytes = ALG_BYTES_PER_POINT_BWD * n_active + 4 * d_raw.shape[-1] * P      # table traffic of the active points + d_raw of all
+    alg_bytes = ALG_BYTES_PER_POINT * P
     achieved = alg_bytes / (bwd_ms * 1e-3) / 1e9
-    achieved_all = ALG_BYTES_PER_POINT_BWD * P / (bwd_ms * 1e-3) / 1e9
+    step_ms = dev_ms / args.steps
+    step_bytes = 2 * ALG_BYTES_PER_POINT * P + ADAM_BYTES_PER_PARAM * n_params + (28 + 4 * S + 44) * R_RAYS     # 651.3 MB
+    traffic = ncu_traffic()
     roof = {"bound": "hbm", "kernel": "field_bwd_tc_kernel (tcgen05 recompute-forward + dgrad + wgrad + grid scatter)",
             "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, ncu --set full
-            # (profiles/r1_final_summary.md): 92.35 MB + 25.06 MB; below the algorithmic bytes because the table is L2 resident
-            "traffic": 117.41e6, "traffic_unit": "bytes/launch",
-            "peak_source": which, "ms_per_launch": bwd_ms, "alg_bytes_per_launch": alg_bytes,
+            "traffic": traffic.get("field_bwd_tc_kernel"), "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum, "
+            "ncu --set full, profiles/r2_ncu_traffic.json)", "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
+            "ms_per_launch": bwd_ms, "alg_bytes_per_launch": alg_bytes, "alg_bytes_per_point": ALG_BYTES_PER_POINT,
             "points_per_launch": P, "active_points_per_launch": n_active,
-            "note": "achieved counts 2,048 B for the ACTIVE points only (+ 40 B of d_raw for every point); with SURVEY 8d's "
-                    "2,048 B x all points the same launch reads as achieved_all_points",
-            "achieved_all_points": achieved_all, "frac_all_points": achieved_all / hbm,
-            "phase_ms": phase_ms,
-            "adam_gbs": ADAM_BYTES_PER_PARAM * (9014144 + 36577) / (phase_ms.get("adam", float("nan")) * 1e-3) / 1e9,
-            "fwd_gbs": ALG_BYTES_PER_POINT_FWD * P / (phase_ms.get("field_fwd", float("nan")) * 1e-3) / 1e9}
+            "step": {"alg_bytes": step_bytes, "ms": step_ms, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
+                     "frac": step_bytes / (step_ms * 1e-3) / 1e9 / hbm,
+                     "what": "2,048 B x points (gather + scatter) + 32 B x parameters (Adam) + ray I/O over the whole map step"},
+            "kernels": {
+                "field_fwd_tc3_kernel": {"alg_bytes": ALG_BYTES_PER_POINT * P, "ms": fwd_ms,
+                                         "achieved": ALG_BYTES_PER_POINT * P / (fwd_ms * 1e-3) / 1e9,
+                                         "frac": ALG_BYTES_PER_POINT * P / (fwd_ms * 1e-3) / 1e9 / hbm,
+                                         "traffic": traffic.get("field_fwd_tc3_kernel")},
+                "adam_pair_kernel": {"alg_bytes": ADAM_BYTES_PER_PARAM * n_params, "ms": phase_ms.get("adam"),
+                                     "achieved": ADAM_BYTES_PER_PARAM * n_params / (phase_ms.get("adam", float("nan")) * 1e-3) / 1e9,
+                                     "frac": ADAM_BYTES_PER_PARAM * n_params / (phase_ms.get("adam", float("nan")) * 1e-3) / 1e9 / hbm,
+                                     "note": "phase = Adam (grid + decoder, one launch) + weight re-layout",
+                                     "traffic": traffic.get("adam_pair_kernel")}},
+            "phase_ms": phase_ms}
+    for k in ("ro_field_query", "joint_query"):
+        if k in also_roof:
+            also_roof[k]["frac"] = also_roof[k]["achieved"] / hbm
+            roof["kernels"][k] = also_roof[k]
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         n_rays, steps = R_RAYS, 3
@@ -318,9 +358,11 @@ def run_gpu(args):
         cpu = {"value": n_rays * steps / dt, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{steps} steps x {n_rays} rays x {S} samples (the full batch), full T=2^19 grid + dense Adam, "
                          f"oracle port of the reference's PyTorch path, torch {torch.__version__}"}
+        # the other metrics of BASELINE.json beside their GPU numbers: tracking, ms/frame, joint query
+        cpu["also"] = cpu_also_baselines(cfg, also)
     out = {"metric": "map_step_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+           "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": workload_config(world),
            "roofline": roof, "cpu_baseline": cpu,
            "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                    "api": "FusedMapper.step_host(rays7 (R,7) pinned host batch, pose_idx, poses) -> ray generation + map step -> 8 loss terms on the host"},
@@ -375,9 +417,115 @@ def tracking_bench(model, cfg, dev, iters=5, group=None):
     b.record(); torch.cuda.synchronize()
     ms_it = _max_over_ranks(a.elapsed_time(b) / iters, dev, group)
     model.train()
-    return {"tracking_pose_candidates_per_s": Cn / (ms_it * 1e-3), "tracking_ms_per_ro_iteration": ms_it,
+    P_ = nr * nc
+    ro_bytes = Cn * (P_ * (ALG_BYTES_PER_POINT + 12) + 28)          # per candidate Pix x (1,024 B + 12 B) + 28 B
+    roof = {"alg_bytes": ro_bytes, "ms": ms_it, "achieved": ro_bytes / (ms_it * 1e-3) / 1e9,
+            "what": "one RandomOptimizer iteration (pose kernel + SDF-only field query + per-candidate reduction + swarm update) "
+                    f"at {Cn} candidates x {P_} pixels; per candidate Pix x 1,036 B + 28 B"}
+    return {"_roof_ro_field_query": roof,
+            "tracking_pose_candidates_per_s": Cn / (ms_it * 1e-3), "tracking_ms_per_ro_iteration": ms_it,
             "tracking_shape": f"{Cn} candidates x {nr * nc} pixels, SDF-only field query + per-candidate reduction + swarm update"
                               + ("" if group is None else "; the candidates are sharded across the GPUs (strong scaling)")}
+
+
+def cpu_also_baselines(cfg, also):
+    """CPU (oracle port, all host threads) numbers for the metrics reported under `also`, each on a bounded sample:
+    one RandomOptimizer iteration at 256 of the 1024 candidates x 2048 pixels; the reference's per-frame work at its shipped
+    sizes (RO 5 x 2000 x 384, 10 pose-refinement iterations x 1000 rays x 75, 15 mapping iterations x 2600 x 75 every 3rd
+    frame), each component timed once; the joint query on a 128^3 sub-grid x 16 submaps (x 64 = 512^3)."""
+    import types
+    import numpy as np
+    import torch
+    import helpers as H
+    from mipsfusion_b200 import synth
+    from oracle import ro as oro, sampling as osamp, joint_query as ojq, adam as oadam
+    out = {"cores": torch.get_num_threads(), "kind": "port"}
+    dirs = synth.camera_rays()
+    c2w = synth.trajectory(4)[1]
+    # ---- C2: RandomOptimizer iteration ----
+    _, of = build_model()
+    Cn, nr, nc, sub = 1024, 32, 64, 256
+    rows, cols = osamp.sample_pixels_uniformly(460, 620, nr, nc)
+    fr = synth.render_frame(c2w, dirs[rows, cols][None].contiguous())
+    g = torch.Generator().manual_seed(0)
+    particles = torch.randn(Cn, 6, generator=g).clamp(-2, 2); particles[0] = 0
+    td, rdc = fr["depth"].reshape(-1, 1), dirs[rows, cols].contiguous()
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        oro.ro_iteration(of, c2w[:3, :3], c2w[:3, 3:], 0.02, particles[:sub], td, rdc, cfg["training"]["trunc"])
+        dt = time.perf_counter() - t0
+    out["tracking_pose_candidates_per_s"] = sub / dt
+    out["tracking_sample"] = f"1 RandomOptimizer iteration, {sub} of the {Cn} candidates x {nr * nc} pixels"
+    if "tracking_pose_candidates_per_s" in also:
+        out["tracking_gpu_over_cpu"] = also["tracking_pose_candidates_per_s"] / out["tracking_pose_candidates_per_s"]
+    # ---- ms / frame at the reference's shipped sizes ----
+    fcfg = H.make_config(HASH, n_samples_d=50, n_range_d=25)
+    off = H.oracle_field(fcfg)
+    frame = synth.render_frame(c2w, dirs)
+    rows, cols = osamp.sample_pixels_uniformly(460, 620, 16, 24)
+    g = torch.Generator().manual_seed(1)
+    p2000 = torch.randn(2000, 6, generator=g).clamp(-2, 2); p2000[0] = 0
+    td, rdc = frame["depth"][rows, cols].reshape(-1, 1), dirs[rows, cols].contiguous()
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        oro.ro_iteration(off, c2w[:3, :3], c2w[:3, 3:], 0.02, p2000, td, rdc, fcfg["training"]["trunc"])
+        t_ro = (time.perf_counter() - t0) * 5                        # 5 RO iterations per frame
+    idx = torch.randint(0, 460 * 620, (1000,), generator=g)
+    r_, c_ = idx // 620, idx % 620
+    d_cam, t_rgb, t_d = dirs[r_, c_], frame["rgb"][r_, c_], frame["depth"][r_, c_].unsqueeze(-1)
+    trans = c2w[:3, 3].clone().requires_grad_(True); rot = c2w[:3, :3].clone().requires_grad_(True)
+    popt = torch.optim.Adam([rot, trans], lr=1e-3)
+    u = torch.rand(1000, 75, generator=g)
+    t0 = time.perf_counter()
+    for _ in range(2):                                               # 2 of the 10 pose-refinement iterations
+        popt.zero_grad()
+        ret = off.forward(trans[None, :].repeat(1000, 1), torch.sum(d_cam[..., None, :] * rot[None], -1), t_rgb, t_d, u, EMD_w=0.0)
+        off.total_loss(ret).backward()
+        popt.step()
+    t_go = (time.perf_counter() - t0) * 5
+    for q in off.parameters():
+        q.grad = None
+    mopt = oadam.make_optimizer(off)
+    idx = torch.randint(0, 460 * 620, (2600,), generator=g)
+    r_, c_ = idx // 620, idx % 620
+    ro_ = c2w[None, :3, 3].repeat(2600, 1); rd_ = torch.sum(dirs[r_, c_][..., None, :] * c2w[None, :3, :3], -1)
+    u = torch.rand(2600, 75, generator=g)
+    t0 = time.perf_counter()
+    for _ in range(2):                                               # 2 of the 15 mapping iterations
+        mopt.zero_grad()
+        off.total_loss(off.forward(ro_, rd_, frame["rgb"][r_, c_], frame["depth"][r_, c_].unsqueeze(-1), u)).backward()
+        mopt.step()
+    t_map = (time.perf_counter() - t0) * 7.5
+    out["ms_per_frame_640x480"] = 1e3 * (t_ro + t_go + t_map / 3.0)
+    out["frame_sample"] = ("RO: 1 of 5 iterations (2000 x 384) x 5; pose refinement: 2 of 10 iterations (1000 rays x 75) x 5; mapping: "
+                           "2 of 15 iterations (2600 rays x 75) x 7.5, every 3rd frame; components "
+                           f"{1e3 * t_ro:.0f} + {1e3 * t_go:.0f} + {1e3 * t_map:.0f}/3 ms")
+    if "ms_per_frame_640x480" in also:
+        out["frame_cpu_over_gpu"] = out["ms_per_frame_640x480"] / also["ms_per_frame_640x480"]
+    # ---- C5: joint query, 128^3 sub-grid x 16 submaps (scaled x 64 to 512^3) ----
+    jcfg = H.make_config(HASH)
+    jcfg["grid"]["use_bound_normalize"] = False
+    jf = H.oracle_field(jcfg)
+    lo, hi = np.array([-0.6, 0.5, -1.15]), np.array([2.95, 7.05, 3.05])
+    ext = hi - lo
+    poses, amin, amax, cents = [], [], [], []
+    for m in range(16):
+        ix, iy = m % 4, m // 4
+        a = lo + ext * np.array([ix / 4.0 - 0.08, iy / 4.0 - 0.08, 0.0])
+        b = lo + ext * np.array([(ix + 1) / 4.0 + 0.08, (iy + 1) / 4.0 + 0.08, 1.0])
+        T = torch.eye(4); T[:3, 3] = torch.tensor((a + b) / 2, dtype=torch.float32)
+        poses.append(T); amin.append(a); amax.append(b); cents.append(((a + b) / 2).astype(np.float32))
+    axes = [np.linspace(lo[k], hi[k], 128) for k in range(3)]
+    xx, yy, zz = np.meshgrid(*axes)
+    pts = np.vstack([xx.ravel(), yy.ravel(), zz.ravel()]).T.astype(np.float32)
+    t0 = time.perf_counter()
+    ojq.joint_query(pts, [jf] * 16, poses, amin, amax, cents)
+    dt = time.perf_counter() - t0
+    out["joint_query_grid_points_per_s"] = pts.shape[0] / dt
+    out["joint_query_sample"] = "128^3 grid over the same volume x 16 submaps (1/64 of the 512^3 points; same submaps-per-point ratio)"
+    if "joint_query_grid_points_per_s" in also:
+        out["joint_query_gpu_over_cpu"] = also["joint_query_grid_points_per_s"] / out["joint_query_grid_points_per_s"]
+    return out
 
 
 def emit(obj):
@@ -451,8 +599,17 @@ def joint_query_bench(dev, res=512, n_submaps=16, group=None):
     torch.cuda.synchronize()
     dt = _max_over_ranks(time.perf_counter() - t0, dev, group)
     frac = float(out["mask"].float().mean())
+    # (point, containing submap) pairs: the boxes are axis aligned, so the count factorises over the axes
+    evals = float(sum(np.prod([np.count_nonzero((axes[k] >= amin[m][k]) & (axes[k] <= amax[m][k])) for k in range(3)])
+                      for m in range(n_submaps)))
     del out
-    return {"joint_query_grid_points_per_s": res ** 3 / dt, "joint_query_s": dt,
+    roof = None
+    if evals is not None:
+        jb = evals * (ALG_BYTES_PER_POINT + 8)                        # per point per containing submap 1,024 B + 8 B out
+        roof = {"alg_bytes": jb, "ms": dt * 1e3, "achieved": jb / dt / 1e9, "evals": evals,
+                "what": f"{res}^3 grid x {n_submaps} submaps: containment + SDF-only field query of every (point, containing submap) "
+                        "pair + blend; per pair 1,032 B" + ("" if group is None else " (all ranks)")}
+    return {"_roof_joint_query": roof, "joint_query_grid_points_per_s": res ** 3 / dt, "joint_query_s": dt,
             "joint_query_shape": f"{res}^3 grid x {n_submaps} submaps (T=2^{HASH} each), {frac:.2f} of the points inside >= 1 submap"
                                  + ("" if group is None else "; the grid points are sharded across the GPUs (strong scaling, results stay sharded)")}
 

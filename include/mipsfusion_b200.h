@@ -95,6 +95,11 @@ int mf_debug_umma_wgrad(const float* dz, const float* x, float* out, int Kf, int
 
 /* Diagnostics: switch the in-kernel clock stamps of the tensor-core backward on/off and read the last ones. */
 int mf_debug_profile(int on, long long* out_host);
+/* Diagnostics for bench.py's roofline line: when on, the launchers bracket the dominant kernel itself with a CUDA event pair
+ * on the launching stream (slot 0 field forward, 1 field backward, 2 RandomOptimizer field query, 3 joint-query field query);
+ * mf_debug_kernel_ms waits for the last bracketed launch of `slot` and returns its duration. */
+int mf_debug_kernel_timer(int on);
+int mf_debug_kernel_ms(int slot, float* ms);
 
 /* ---- a1: hash-grid encoding (replaces tcnn.Encoding "HashGrid", model/encodings.py:14-25) ---- */
 int mf_hashgrid_meta(int log2_hashmap_size, int n_levels, int n_features, int base_resolution,

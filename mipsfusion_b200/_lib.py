@@ -16,6 +16,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mipsfusion_b200.h
 MF_MAX_LEVELS = 16
 MF_MLP_PARAMS = 36577
 MF_RAW_DIM = 10
+MF_MAX_SAMPLES = 128          # render_kernels.cu MAX_S
 
 
 class GridMeta(C.Structure):
@@ -59,6 +60,8 @@ PROTOTYPES = {
     "mf_debug_umma_dgrad": (_I, [_P, _P, _P, _I, _P]),
     "mf_debug_umma_wgrad": (_I, [_P, _P, _P, _I, _I, _P]),
     "mf_debug_profile": (_I, [_I, _P]),
+    "mf_debug_kernel_timer": (_I, [_I]),
+    "mf_debug_kernel_ms": (_I, [_I, _P]),
     "mf_hashgrid_meta": (_I, [_I, _I, _I, _I, _D, C.POINTER(GridMeta)]),
     "mf_hashgrid_fwd": (_I, [_P, _P, C.POINTER(GridMeta), _P, _P, _L, _P]),
     "mf_hashgrid_bwd": (_I, [_P, _P, _P, C.POINTER(GridMeta), _P, _P, _L, _P]),

@@ -531,6 +531,7 @@ static int launch_field_bwd(const FieldDev& d, const Src& src, const float* d_ra
         const int64_t tiles = (N + TC_TP - 1) / TC_TP;
         const int64_t cap = mf_sm_count_cached();
         const int grid = (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
+        mf_ktimer_begin(1, st);
         if (d_pts) {
             int rc = set_smem(field_bwd_tc_kernel<Src, true>, SMEM_TC_BWD); if (rc) return rc;
             field_bwd_tc_kernel<Src, true><<<grid, TC_NT, SMEM_TC_BWD, st>>>(d, src, d_raw, grad_grid, workspace, d_pts, N, am, mf_tc_error_flag(), mf_tc_profile_buffer());
@@ -538,6 +539,7 @@ static int launch_field_bwd(const FieldDev& d, const Src& src, const float* d_ra
             int rc = set_smem(field_bwd_tc_kernel<Src, false>, SMEM_TC_BWD); if (rc) return rc;
             field_bwd_tc_kernel<Src, false><<<grid, TC_NT, SMEM_TC_BWD, st>>>(d, src, d_raw, grad_grid, workspace, nullptr, N, am, mf_tc_error_flag(), mf_tc_profile_buffer());
         }
+        mf_ktimer_end(1, st);
         MF_LAUNCH_CHECK();
         reduce_partials_kernel<<<(MF_MLP_PARAMS + 31) / 32, 256, 0, st>>>(workspace, grid, grad_mlp, 1);
         MF_LAUNCH_CHECK();
@@ -590,7 +592,7 @@ MF_API int mf_field_query_rays(const float* rays_o, const float* rays_d, const f
     FieldDev d; int rc = mf_field_to_dev(field, &d); if (rc) return rc;
     d.feat = (uint32_t*)feat;
     SrcRays src{rays_o, rays_d, z, S};
-    return launch_field_fwd_auto<SrcRays, EpiRaw, false>(d, src, EpiRaw{raw}, R * S, (cudaStream_t)stream);
+    return launch_field_fwd_auto<SrcRays, EpiRaw, false>(d, src, EpiRaw{raw}, R * S, (cudaStream_t)stream, nullptr, false, 0);
 }
 
 MF_API int mf_field_query_rays_bwd(const float* rays_o, const float* rays_d, const float* z, const mf_field* field,

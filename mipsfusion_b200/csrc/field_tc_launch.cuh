@@ -44,8 +44,22 @@ static inline int launch_field_fwd_tc3(const FieldDev& d, const Src& src, const 
 }
 
 template <class Src, class Epi, bool SDF_ONLY>
+static inline int launch_field_fwd_auto_(const FieldDev& d, const Src& src, const Epi& epi, int64_t N, cudaStream_t st,
+                                         const unsigned int* n_dev, bool short_launches);
+
+// ktimer_slot >= 0: bracket the kernel with the diagnostic event pair of that slot (mf_debug_kernel_timer)
+template <class Src, class Epi, bool SDF_ONLY>
 static inline int launch_field_fwd_auto(const FieldDev& d, const Src& src, const Epi& epi, int64_t N, cudaStream_t st,
-                                        const unsigned int* n_dev = nullptr, bool short_launches = false) {
+                                        const unsigned int* n_dev = nullptr, bool short_launches = false, int ktimer_slot = -1) {
+    if (ktimer_slot >= 0) mf_ktimer_begin(ktimer_slot, st);
+    const int rc = launch_field_fwd_auto_<Src, Epi, SDF_ONLY>(d, src, epi, N, st, n_dev, short_launches);
+    if (ktimer_slot >= 0) mf_ktimer_end(ktimer_slot, st);
+    return rc;
+}
+
+template <class Src, class Epi, bool SDF_ONLY>
+static inline int launch_field_fwd_auto_(const FieldDev& d, const Src& src, const Epi& epi, int64_t N, cudaStream_t st,
+                                         const unsigned int* n_dev, bool short_launches) {
     // short launches (a few tiles per CTA, e.g. the per-submap chunks of the joint query) cannot fill the
     // producer -> consumer pipeline; two independent tiles per CTA (dual pipeline) serve them better
     if (d.impl == 0 && short_launches) return launch_field_fwd_tc2<Src, Epi, SDF_ONLY>(d, src, epi, N, st, n_dev);

@@ -94,3 +94,35 @@ MF_API int mf_debug_profile(int on, long long* out_host) {
     }
     return MF_OK;
 }
+
+// ---- per-kernel device timing (diagnostics; bench.py's roofline line) ----------------------------
+// When enabled, the launchers of the dominant kernels bracket the kernel launch itself with a CUDA event pair on the
+// launching stream (slot 0: field forward, 1: field backward, 2: RandomOptimizer field query, 3: joint-query field query).
+static int g_ktimer_on = 0;
+static cudaEvent_t g_kev[64][MF_KTIMER_SLOTS][2];
+static bool g_kev_init[64] = {false};
+static cudaEvent_t* ktimer_events(int slot) {
+    if (!g_ktimer_on || slot < 0 || slot >= MF_KTIMER_SLOTS) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!g_kev_init[dev]) {
+        for (int s = 0; s < MF_KTIMER_SLOTS; ++s)
+            for (int k = 0; k < 2; ++k)
+                if (cudaEventCreate(&g_kev[dev][s][k]) != cudaSuccess) return nullptr;
+        g_kev_init[dev] = true;
+    }
+    return g_kev[dev][slot];
+}
+void mf_ktimer_begin(int slot, cudaStream_t st) { if (cudaEvent_t* e = ktimer_events(slot)) cudaEventRecord(e[0], st); }
+void mf_ktimer_end(int slot, cudaStream_t st) { if (cudaEvent_t* e = ktimer_events(slot)) cudaEventRecord(e[1], st); }
+
+MF_API int mf_debug_kernel_timer(int on) { g_ktimer_on = on ? 1 : 0; return MF_OK; }
+// Duration (ms) of the last launch bracketed in `slot`.  Waits for that launch to finish.
+MF_API int mf_debug_kernel_ms(int slot, float* ms) {
+    MF_CHECK_ARG(ms != nullptr && slot >= 0 && slot < MF_KTIMER_SLOTS);
+    cudaEvent_t* e = ktimer_events(slot);
+    if (!e) { mf_set_error("mf_debug_kernel_ms: the kernel timer is off"); return MF_ERR_INVALID; }
+    MF_CUDA(cudaEventSynchronize(e[1]));
+    MF_CUDA(cudaEventElapsedTime(ms, e[0], e[1]));
+    return MF_OK;
+}

@@ -31,6 +31,9 @@ void mf_set_error(const char* fmt, ...);
 #define MF_LAUNCH_CHECK() MF_CUDA(cudaGetLastError())
 
 int mf_sm_count_cached();
+constexpr int MF_KTIMER_SLOTS = 4;
+void mf_ktimer_begin(int slot, cudaStream_t st);   // no-ops unless mf_debug_kernel_timer(1)
+void mf_ktimer_end(int slot, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // Tile geometry of the fused field kernels: one CTA works on TP points at a time; activations

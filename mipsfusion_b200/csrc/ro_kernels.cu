@@ -186,7 +186,7 @@ MF_API int mf_ro_score(const float* particles6, const float* search_size, const 
     MF_LAUNCH_CHECK();
     SrcRO src{Rt, dirs_cam, target_d, P};
     EpiAbsSdf epi{vals, target_d, P, (float)trunc};
-    rc = launch_field_fwd_auto<SrcRO, EpiAbsSdf, true>(d, src, epi, (int64_t)c_count * P, st);
+    rc = launch_field_fwd_auto<SrcRO, EpiAbsSdf, true>(d, src, epi, (int64_t)c_count * P, st, nullptr, false, 2);
     if (rc) return rc;
     ro_reduce_kernel<<<(c_count + 7) / 8, 256, 0, st>>>(vals, c_count, P, (float)sdf_weight, fitness, mean_sdf);
     MF_LAUNCH_CHECK();

@@ -101,6 +101,18 @@ class MLP_reg(nn.Module):
     def prepared(self):
         """Kernel-layout weights, rebuilt only when a parameter changed (mf_mlp_prepare)."""
         ps = self.ordered_params()
+        ext = self.__dict__.get("_ext_prep")
+        if ext is not None:
+            # a FusedMapper steps these parameters in place (they are views of its flat master copy) and refreshes its own
+            # kernel-layout image after every step: hand that image out, so every route sees the stepped weights
+            ptrs, owner = ext
+            if tuple(p.data_ptr() for p in ps) == ptrs:
+                vers = tuple(p._version for p in ps)
+                if vers != owner._seen_versions:         # written by somebody else (load_state_dict, another optimiser)
+                    L.call("mf_mlp_prepare", L.ptr(owner.mlp), L.ptr(owner.prep), L.stream())
+                    owner._seen_versions = vers
+                return owner.prep
+            self.__dict__.pop("_ext_prep")
         key = tuple((p.data_ptr(), p._version) for p in ps)
         cache = self.__dict__.get("_prep_cache")
         if cache is None or cache[0] != key:
@@ -117,6 +129,7 @@ class MLP_reg(nn.Module):
     def __getstate__(self):
         s = self.__dict__.copy()
         s.pop("_prep_cache", None)
+        s.pop("_ext_prep", None)
         s.pop("_flat_grad", None)
         s.pop("_ordered", None)
         return s

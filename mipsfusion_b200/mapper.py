@@ -61,6 +61,22 @@ class FusedMapper:
         self.launches = 0
         with torch.cuda.device(self.dev):
             L.call("mf_mlp_prepare", L.ptr(self.mlp), L.ptr(self.prep), L.stream())
+        self._bind_module()
+
+    def _bind_module(self):
+        """The module's ten decoder nn.Parameters become views of the flat master copy the Adam kernel steps, and
+        ``decoder.prepared()`` hands out this mapper's kernel-layout image: after every mapping step RandomOptimizer.score,
+        JointSubmapQuery, JointEncoding.forward and state_dict() all see the stepped grid AND the stepped decoder."""
+        dec, o = self.model.decoder, 0
+        ps = dec.ordered_params()
+        with torch.no_grad():
+            for p in ps:
+                n = p.numel()
+                p.data = self.mlp[o:o + n].view(p.shape)
+                o += n
+        self._seen_versions = tuple(p._version for p in ps)
+        dec.__dict__.pop("_prep_cache", None)
+        dec.__dict__["_ext_prep"] = (tuple(p.data_ptr() for p in ps), self)
 
     def _init_peer_arena(self):
         ng, nm = self.grid.numel(), self.mlp.numel()
@@ -241,10 +257,16 @@ class FusedMapper:
         self.launches += 3            # two sharded updates + weight prepare (the barriers are torch's kernels)
 
     def sync_to_module(self):
-        """Write the stepped decoder weights back into the module's nn.Parameters (the grid is updated in place)."""
-        o = 0
-        with torch.no_grad():
-            for p in self.model.decoder.ordered_params():
-                n = p.numel()
-                p.copy_(self.mlp[o:o + n].view(p.shape))
-                o += n
+        """Kept for callers of the first version: the module's parameters ARE the stepped weights (views of the flat master,
+        see :meth:`_bind_module`), so there is nothing to copy; re-binds if the module's parameters were re-assigned."""
+        ps = self.model.decoder.ordered_params()
+        ext = self.model.decoder.__dict__.get("_ext_prep")
+        if ext is None or ext[1] is not self or tuple(p.data_ptr() for p in ps) != ext[0]:
+            o = 0
+            with torch.no_grad():
+                for p in ps:                                   # adopt whatever the module holds now, then bind again
+                    n = p.numel()
+                    self.mlp[o:o + n].copy_(p.detach().reshape(-1))
+                    o += n
+            L.call("mf_mlp_prepare", L.ptr(self.mlp), L.ptr(self.prep), L.stream())
+            self._bind_module()

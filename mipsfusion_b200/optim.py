@@ -53,6 +53,8 @@ class FusedAdam(torch.optim.Optimizer):
 
 
 def create_map_optimizer(model, lr_decoder, lr_embed):
-    """FusedAdam with the parameter groups of reference mipsfusion.py:580-584."""
+    """FusedAdam with the parameter groups of reference mipsfusion.py:580-584.  Also lets the model's backward kernels add
+    straight into ``.grad`` (scene_rep._grad_targets): this optimiser's loop is backward -> step -> zero_grad."""
+    model.accumulate_grads_in_place = True
     return FusedAdam([{"params": list(model.decoder.parameters()), "weight_decay": 1e-6, "lr": lr_decoder},
                       {"params": list(model.embed_fn.parameters()), "eps": 1e-15, "lr": lr_embed}], betas=(0.9, 0.99))

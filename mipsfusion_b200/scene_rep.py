@@ -74,10 +74,14 @@ def _split(flat, shapes):
 def _grad_targets(model, grid, dev, need_grid, need_mlp):
     """Where the backward kernels accumulate: straight into the parameters' ``.grad`` when that is possible (saves the
     zero-fill of a 36 MB temporary plus autograd's add into ``.grad``, and ten small adds for the decoder), else into fresh
-    tensors that are returned to autograd.  ``loss.backward()`` sees no difference; set
-    ``model.accumulate_grads_in_place = False`` when gradients are taken with ``torch.autograd.grad`` (which must not
-    touch ``.grad``).  -> (g_grid, return_grid, g_mlp, return_mlp)"""
-    in_place = getattr(model, "accumulate_grads_in_place", True)
+    tensors that are returned to autograd.  OFF by default: plain autograd semantics (``torch.autograd.grad``, gradient
+    hooks, ``backward(inputs=...)`` all see the parameter gradients).  ``mipsfusion_b200.create_map_optimizer`` (the fused
+    stand-in for the reference's ``create_optimizer``, mipsfusion.py:580-584) switches it on for the model it is given:
+    that loop is ``loss.backward(); optimizer.step(); zero_grad()``, for which the two are indistinguishable.  A parameter
+    with registered hooks always gets its gradient returned.  -> (g_grid, return_grid, g_mlp, return_mlp)"""
+    in_place = bool(getattr(model, "accumulate_grads_in_place", False))
+    if in_place and (model.embed_fn.params._backward_hooks or any(q._backward_hooks for q in model.decoder.ordered_params())):
+        in_place = False
     p = model.embed_fn.params
     g = p.grad if (in_place and need_grid and p.data_ptr() == grid.data_ptr()) else None
     if g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == grid.shape and g.device == grid.device \
@@ -133,6 +137,7 @@ class _RenderFn(torch.autograd.Function):
         ctx.save_for_backward(rays_o, rays_d, target_rgb, target_d, z, raw, counts, losses, grid)
         ctx.shapes = [p.shape for p in mlp_params]
         ctx.mark_non_differentiable(aux, z, counts)
+        ctx.set_materialize_grads(False)          # unused outputs arrive as None in backward (no dense zero buffers)
         return rgb, depth, aux, z, raw, losses, counts
 
     @staticmethod
@@ -249,6 +254,9 @@ class JointEncoding(nn.Module):
             cfg.n_samples_d, cfg.n_range_d = int(tr["n_samples_d"]), int(tr["n_range_d"])
         else:
             cfg.n_samples_d, cfg.n_range_d = int(tr["n_samples"]), 0
+        if not 0 < cfg.n_samples_d + cfg.n_range_d <= L.MF_MAX_SAMPLES:
+            raise L.MipsFusionB200Error(f"render kernels hold a ray's samples in registers: 1..{L.MF_MAX_SAMPLES} samples per ray, "
+                                        f"got {cfg.n_samples_d + cfg.n_range_d}")
         cfg.perturb = 1 if tr["perturb"] > 0.0 else 0
         cfg.rgb_missing_nz = 1 if tr["rgb_missing"] != 0 else 0
         cfg.trunc, cfg.sc_factor = float(tr["trunc"]), float(self.config["data"]["sc_factor"])

@@ -1,0 +1,41 @@
+"""Runs one path a few times so that ncu can capture its dominant kernel:
+    python scripts/prof_kernels.py ro|jq|go|map [iters]
+ro: RandomOptimizer scoring at 1024 candidates x 2048 pixels (field_fwd_tc3_kernel<SrcRO, EpiAbsSdf, SDF_ONLY>)
+jq: joint query, 128^3 grid x 16 submaps (field_fwd_tc2_kernel<SrcJoint, ...>)
+go: gradient pose refinement, 1000 rays x 75 samples with ray gradients (the pose-gradient backward)
+map: the C1 map step (FusedMapper.step)"""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bench, helpers as H
+mode = sys.argv[1]
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+dev = torch.device("cuda", 0)
+if mode == "ro":
+    cfg, of = bench.build_model()
+    model = H.cuda_model(cfg, H.state_of(of))
+    print(bench.tracking_bench(model, cfg, dev, iters=iters))
+elif mode == "jq":
+    print(bench.joint_query_bench(dev, res=128))
+elif mode == "go":
+    cfg = H.make_config(bench.HASH, n_samples_d=50, n_range_d=25)
+    of = H.oracle_field(cfg); model = H.cuda_model(cfg, H.state_of(of))
+    rays_o, rays_d, rgb, d, u = [t.to(dev) for t in H.synth_batch(1000, 75, seed=2)]
+    tw = cfg["training"]
+    for _ in range(iters):
+        ro_, rd_ = rays_o.clone().requires_grad_(True), rays_d.clone().requires_grad_(True)
+        ret = model(ro_, rd_, rgb, d, EMD_w=0.0, u=u)
+        (tw["rgb_weight"] * ret["rgb_loss"] + tw["sdf_weight"] * ret["sdf_loss"] + tw["fs_weight"] * ret["fs_loss"]).backward()
+    torch.cuda.synchronize()
+    print("go ok", float(ro_.grad.abs().sum()))
+elif mode == "map":
+    from mipsfusion_b200.mapper import FusedMapper
+    cfg, of = bench.build_model()
+    model = H.cuda_model(cfg, H.state_of(of))
+    rays_o, rays_d, rgb, d, _ = [t.to(dev).contiguous() for t in bench.make_inputs(0)]
+    mapper = FusedMapper(model)
+    for _ in range(iters):
+        losses = mapper.step(rays_o, rays_d, rgb, d.reshape(-1))
+    torch.cuda.synchronize()
+    print("map ok", losses.tolist())

@@ -184,16 +184,21 @@ def test_joint_query_vs_oracle():
     contain64 = np.stack([np.all((p64 >= amin[i]) & (p64 <= amax[i]), -1) for i in range(3)], -1)
     res = jq.query(axes=axes, vis=vis, want_contain=True)
     assert np.array_equal(res["contain"].cpu().numpy(), contain64)                  # submap assignment: bit exact
-    same = np.array_equal(contain64, res_o["contain"])
     assert np.array_equal(res["mask"].cpu().numpy(), (contain64 & vis).any(-1))
-    if same:
-        assert H.rel_err(res["sdf"].cpu().numpy(), res_o["sdf"]) < 2e-3
+    # the oracle tests containment on the fp32-rounded points: compare the fields wherever both assign the same submaps
+    # (all points of this fixture; the floor below keeps the comparison from silently shrinking)
+    agree = (contain64 == res_o["contain"]).all(-1)
+    assert agree.mean() > 0.999, agree.mean()
+    err = H.rel_err(res["sdf"].cpu().numpy()[agree], res_o["sdf"][agree])
+    assert err < 1e-3, err
     # explicit points (vertex colour pass)
     sel = rng.choice(G, 500, replace=False)
     res_c = jq.query(points=pts64[sel], vis=vis[sel], color=True)
     res_co = ojq.joint_query(pts64[sel].astype(np.float32), fields, poses, amin, amax, cents, vis_masks=vis[sel], color=True)
-    if np.array_equal(np.stack([np.all((pts64[sel] >= amin[i]) & (pts64[sel] <= amax[i]), -1) for i in range(3)], -1), res_co["contain"]):
-        assert H.rel_err(res_c["rgb"].cpu().numpy(), res_co["rgb"]) < 2e-3
+    agree_c = (np.stack([np.all((pts64[sel] >= amin[i]) & (pts64[sel] <= amax[i]), -1) for i in range(3)], -1) == res_co["contain"]).all(-1)
+    assert agree_c.mean() > 0.99, agree_c.mean()
+    err_c = H.rel_err(res_c["rgb"].cpu().numpy()[agree_c], res_co["rgb"][agree_c])
+    assert err_c < 1e-3, err_c
     # no submap sees the point -> -1 / masked
     far = jq.query(points=np.array([[50.0, 50.0, 50.0]]))
     assert float(far["sdf"][0]) == -1.0 and not bool(far["mask"][0])

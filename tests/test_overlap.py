@@ -35,12 +35,23 @@ def _run(models, fx, dev):
     return a, (float(loss2), f1.grad.cpu().numpy().copy(), f2.grad.cpu().numpy().copy())
 
 
-def _check(got, fx, tol, gtol=None):
+def _check(got, fx, tol, gtol=None, one_flip=None):
+    """one_flip: allow at most ONE of the four pose-gradient matrices to miss gtol, and only with the signature of a single
+    sample whose grid cell flipped: the error matrix is rank one (every sample adds an outer product row x [point, 1] to
+    d loss / d pose) and stays below `one_flip`."""
     (l1, g11, g12), (l2, g21, g22) = got
     np.testing.assert_allclose(l1, float(fx["loss"]), rtol=tol)
     np.testing.assert_allclose(l2, float(fx["loss2"]), rtol=tol)
+    flipped = []
     for g, k in ((g11, "g_first1"), (g12, "g_first2"), (g21, "g2_first1"), (g22, "g2_first2")):
-        assert H.rel_err(g, fx[k]) < (gtol or tol), (k, H.rel_err(g, fx[k]))
+        err = H.rel_err(g, fx[k])
+        if err < (gtol or tol):
+            continue
+        assert one_flip is not None and err < one_flip, (k, err)
+        sv = np.linalg.svd(np.asarray(g, np.float64) - np.asarray(fx[k], np.float64), compute_uv=False)
+        assert sv[1] < 2e-2 * sv[0], (k, err, sv)           # rank one: one sample
+        flipped.append(k)
+    assert len(flipped) <= 1, flipped
 
 
 def test_oracle_overlap_matches_reference():
@@ -59,6 +70,7 @@ def test_gpu_overlap_matches_reference():
     # 1e-5.  The fourth differs by 3.2e-2 (max-norm) with a RANK-ONE error pattern = one sample: torch's matrix inverse gives
     # a last-ulp different local pose on the GPU, one sample of this fixture sits on a cell boundary of a fine grid level, its
     # floor() flips, and the trilinear interpolant's gradient is discontinuous there (the value is continuous: the loss is
-    # unaffected).  With 96 points x 2 models x 16 levels x 3 axes about one such event is expected.  Hence: loss at 1e-3,
-    # gradients bounded at 5e-2 (one flipped sample), not at the 1e-5 the other matrices reach.
-    _check(_run(models, fx, "cuda"), fx, 1e-3, gtol=5e-2)
+    # unaffected).  With 96 points x 2 models x 16 levels x 3 axes about one such event is expected.  Hence: losses at 1e-3,
+    # gradients at 1e-4, and at most one matrix may differ -- by a rank-one matrix (= one sample) below 5e-2; _check asserts
+    # exactly that structure.
+    _check(_run(models, fx, "cuda"), fx, 1e-3, gtol=1e-4, one_flip=5e-2)
