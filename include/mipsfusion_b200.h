@@ -83,6 +83,8 @@ int mf_set_decoder_impl(int impl);
 int mf_get_decoder_impl(void);
 /* 1 if a tensor-core kernel reported an MMA-completion timeout since the last call (clears the flag;
  * synchronises the device -- diagnostics only). */
+/* A/B switch of the tensor-core backward: 0 = role-split kernel (default), 1 = single-role kernel of round 1. */
+int mf_set_bwd_impl(int impl);
 int mf_tc_check_error(void);
 /* Diagnostics: out (128,128) = x (128,K) w (128,K)^T through one tcgen05 layer; K % 16 == 0, K <= 128;
  * passes = 1 (bf16) or 3 (bf16x3 split). */

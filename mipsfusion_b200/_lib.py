@@ -55,6 +55,7 @@ PROTOTYPES = {
     "mf_device_sm_count": (_I, []),
     "mf_set_decoder_impl": (_I, [_I]),
     "mf_get_decoder_impl": (_I, []),
+    "mf_set_bwd_impl": (_I, [_I]),
     "mf_tc_check_error": (_I, []),
     "mf_debug_umma_linear": (_I, [_P, _P, _P, _I, _I, _P]),
     "mf_debug_umma_dgrad": (_I, [_P, _P, _P, _I, _P]),

@@ -4,6 +4,7 @@
 #include "field_launch.cuh"
 #include "field_tc_launch.cuh"
 #include "field_tc_bwd.cuh"
+#include "field_tc_bwd2.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Weight re-layout (runs once per optimiser step; 36.6 k floats).
@@ -164,9 +165,34 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_kernel(const float* embed, cons
 // CTAs j, j+8, ... in order (coalesced 128-byte reads), then the 8 partial sums are combined in a fixed order ->
 // deterministic.  transposed != 0: the three 128-row weight matrices are stored [in][out] inside each partial
 // (tensor-core path) and dst() undoes that.
+// transposed == 2 (role-split tensor-core backward): additionally, the LAST block forms the gradient of pts_linear.2.bias, which
+// that kernel does not accumulate per point because it is linear in two other bias gradients of the same call:
+//   dH[p][n] = sum_m dZ3[p][m] Ws1[m][n] (n < 64),  dH[p][n] = sum_c dRGB[p][c] Wr[c][n - 64] (n >= 64)
+//   =>  db2[n] = sum_m dbs1[m] Ws1[m][n]  resp.  sum_c dbr[c] Wr[c][n - 64];      mlp = the state_dict-ordered weight blob.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int n_cta, float* __restrict__ grad_mlp,
-                                                              int transposed) {
+                                                              int transposed, const float* __restrict__ mlp) {
     __shared__ float acc[8][32];
+    if (transposed == 2 && blockIdx.x == gridDim.x - 1) {
+        __shared__ float dbs1[D_H], dbr[4];
+        const int t = threadIdx.x;
+        if (t < D_H + 3) {
+            const int sidx = t < D_H ? OFF_BS1 + t : OFF_BR + (t - D_H);
+            float s = 0.f;
+            for (int c = 0; c < n_cta; ++c) s += __ldg(&part[(size_t)c * MF_MLP_PARAMS + sidx]);
+            if (t < D_H) dbs1[t] = s; else dbr[t - D_H] = s;
+        }
+        __syncthreads();
+        if (t < D_H) {
+            float s = 0.f;
+            if (t < D_SDF_EMB) {
+                for (int m = 0; m < D_H; ++m) s = fmaf(dbs1[m], __ldg(&mlp[OFF_WS1 + m * D_SDF_IN + t]), s);
+            } else {
+                for (int c = 0; c < 3; ++c) s = fmaf(dbr[c], __ldg(&mlp[OFF_WR + c * D_RGB_IN + (t - D_SDF_EMB)]), s);
+            }
+            grad_mlp[OFF_B2 + t] += s;
+        }
+        return;
+    }
     const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
     const int sidx = blockIdx.x * 32 + lane;
     const bool on = sidx < MF_MLP_PARAMS;
@@ -177,7 +203,8 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     }
     acc[j][lane] = s;
     __syncthreads();
-    if (j == 0 && on) {
+    const bool b2_entry = transposed == 2 && sidx >= OFF_B2 && sidx < OFF_B2 + D_H;      // owned by the last block
+    if (j == 0 && on && !b2_entry) {
         const float tot = ((acc[0][lane] + acc[1][lane]) + (acc[2][lane] + acc[3][lane])) + ((acc[4][lane] + acc[5][lane]) + (acc[6][lane] + acc[7][lane]));
         int dst = sidx;
         if (transposed) {
@@ -431,7 +458,7 @@ MF_API int mf_mlp_bwd(const float* embed, const float* embed_pos, const float* p
         mlp_bwd_kernel<false><<<grid, NT, SMEM_BWD, st>>>(embed, embed_pos, pts, mlp_prep, d_out, workspace, d_embed, nullptr, nullptr, N);
     }
     MF_LAUNCH_CHECK();
-    reduce_partials_kernel<<<(MF_MLP_PARAMS + 31) / 32, 256, 0, st>>>(workspace, grid, grad_mlp, 0);
+    reduce_partials_kernel<<<(MF_MLP_PARAMS + 31) / 32, 256, 0, st>>>(workspace, grid, grad_mlp, 0, nullptr);
     MF_LAUNCH_CHECK();
     return MF_OK;
 }
@@ -515,9 +542,12 @@ static int compact_active_points(const float* d_raw, int64_t N, float* scratch, 
     return MF_OK;
 }
 
+// ... followed by the CTA-private scratch of the role-split tensor-core backward (parked activations, field_tc_bwd2.cuh)
+static inline int64_t cta_scratch_words() { return (int64_t)mf_sm_count_cached() * b2::SCR_CTA_WORDS; }
+
 MF_API int64_t mf_field_bwd_workspace_size(int64_t n_points, int want_point_grads) {
     if (n_points < 0) n_points = 0;
-    return mf_mlp_grad_workspace_size() + (want_point_grads ? 3 * n_points : 0) + act_scratch_words(n_points);
+    return mf_mlp_grad_workspace_size() + (want_point_grads ? 3 * n_points : 0) + act_scratch_words(n_points) + cta_scratch_words();
 }
 
 template <class Src>
@@ -532,6 +562,16 @@ static int launch_field_bwd(const FieldDev& d, const Src& src, const float* d_ra
         const int64_t cap = mf_sm_count_cached();
         const int grid = (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
         mf_ktimer_begin(1, st);
+        if (!d_pts && mf_bwd_impl() == 0) {                // role-split kernel (parameter gradients only)
+            int rc = set_smem(field_bwd_tc2_kernel<Src>, b2::SMEM); if (rc) return rc;
+            uint32_t* cta_scr = reinterpret_cast<uint32_t*>(scratch + act_scratch_words(N));
+            field_bwd_tc2_kernel<Src><<<grid, b2::B2_NT, b2::SMEM, st>>>(d, src, d_raw, grad_grid, workspace, cta_scr, N, am, mf_tc_error_flag(), mf_tc_profile_buffer());
+            mf_ktimer_end(1, st);
+            MF_LAUNCH_CHECK();
+            reduce_partials_kernel<<<(MF_MLP_PARAMS + 31) / 32 + 1, 256, 0, st>>>(workspace, grid, grad_mlp, 2, d.prep);
+            MF_LAUNCH_CHECK();
+            return MF_OK;
+        }
         if (d_pts) {
             int rc = set_smem(field_bwd_tc_kernel<Src, true>, SMEM_TC_BWD); if (rc) return rc;
             field_bwd_tc_kernel<Src, true><<<grid, TC_NT, SMEM_TC_BWD, st>>>(d, src, d_raw, grad_grid, workspace, d_pts, N, am, mf_tc_error_flag(), mf_tc_profile_buffer());
@@ -541,7 +581,7 @@ static int launch_field_bwd(const FieldDev& d, const Src& src, const float* d_ra
         }
         mf_ktimer_end(1, st);
         MF_LAUNCH_CHECK();
-        reduce_partials_kernel<<<(MF_MLP_PARAMS + 31) / 32, 256, 0, st>>>(workspace, grid, grad_mlp, 1);
+        reduce_partials_kernel<<<(MF_MLP_PARAMS + 31) / 32, 256, 0, st>>>(workspace, grid, grad_mlp, 1, nullptr);
         MF_LAUNCH_CHECK();
         return MF_OK;
     }
@@ -554,7 +594,7 @@ static int launch_field_bwd(const FieldDev& d, const Src& src, const float* d_ra
         field_bwd_kernel<Src, false><<<grid, NT, SMEM_BWD, st>>>(d, src, d_raw, grad_grid, workspace, nullptr, N, am);
     }
     MF_LAUNCH_CHECK();
-    reduce_partials_kernel<<<(MF_MLP_PARAMS + 31) / 32, 256, 0, st>>>(workspace, grid, grad_mlp, 0);
+    reduce_partials_kernel<<<(MF_MLP_PARAMS + 31) / 32, 256, 0, st>>>(workspace, grid, grad_mlp, 0, nullptr);
     MF_LAUNCH_CHECK();
     return MF_OK;
 }

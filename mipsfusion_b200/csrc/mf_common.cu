@@ -47,6 +47,15 @@ MF_API int mf_set_decoder_impl(int impl) {
 }
 MF_API int mf_get_decoder_impl(void) { return g_decoder_impl; }
 
+// A/B switch of the tensor-core backward: 0 role-split kernel (field_tc_bwd2.cuh, default), 1 single-role kernel.
+static int g_bwd_impl = 0;
+int mf_bwd_impl() { return g_bwd_impl; }
+MF_API int mf_set_bwd_impl(int impl) {
+    MF_CHECK_ARG(impl == 0 || impl == 1);
+    g_bwd_impl = impl;
+    return MF_OK;
+}
+
 static int* g_tc_err[64] = {nullptr};
 int* mf_tc_error_flag() {
     int dev = 0;

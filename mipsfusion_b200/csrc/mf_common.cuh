@@ -107,6 +107,7 @@ struct ActiveMap {
 
 int mf_field_to_dev(const mf_field* f, FieldDev* d);   // validates (16 levels, 2 features)
 int mf_decoder_impl();                                 // 0: tcgen05 tensor cores (default), 1: fp32 CUDA cores
+int mf_bwd_impl();                                     // tensor-core backward: 0 role-split kernel (default), 1 single-role kernel
 int* mf_tc_error_flag();
 long long* mf_tc_profile_buffer();                     // device buffer of 64 clock stamps, or nullptr when profiling is off                               // device int, set by a kernel whose MMA wait timed out
 

@@ -48,10 +48,14 @@ __global__ void ro_pose_kernel(const float* __restrict__ particles6, const float
     for (int k = 0; k < 6; ++k) s[1 + k] = p[k];
 }
 
+// Point order of the scoring launch is PIXEL-major: i = pixel * C + candidate.  The 32 lanes of a warp (and the 128 points of a
+// tile) are candidates of the same pixel: poses a few centimetres apart, so on the coarse and middle levels they fall into the
+// same or neighbouring grid cells and their table gathers coalesce into a few cache lines instead of 32 (the gather stage of the
+// forward kernel is bound by L1 wavefronts, one per distinct line).  Each point is still evaluated independently of its tile.
 struct SrcRO {                             // world point of (candidate, pixel): R_c (d_cam * depth) + t_c
-    const float* Rt; const float* dirs; const float* depth; int P;
+    const float* Rt; const float* dirs; const float* depth; int C;
     __device__ __forceinline__ void point(int64_t i, const FieldDev& f, float x[3]) const {
-        const int64_t c = i / P; const int p = (int)(i % P);
+        const int p = (int)(i / C); const int64_t c = i % C;
         const float dp = depth[p];
         const float cam[3] = {__fmul_rn(dirs[p * 3], dp), __fmul_rn(dirs[p * 3 + 1], dp), __fmul_rn(dirs[p * 3 + 2], dp)};
         const float* R = Rt + c * 12;
@@ -63,29 +67,38 @@ struct SrcRO {                             // world point of (candidate, pixel):
     }
 };
 
-struct EpiAbsSdf {                         // valid * |sdf * trunc| per (candidate, pixel)
-    float* out; const float* depth; int P; float trunc;
+struct EpiAbsSdf {                         // valid * |sdf * trunc| per (pixel, candidate)
+    float* out; const float* depth; int C; float trunc;
     __device__ __forceinline__ void store(const float* OUT, int ld, int tp, int64_t tile, int64_t N, int tid, int nthreads) const {
         const int m = tid;
         const int64_t i = tile * tp + m;
         if (m < tp && i < N) {
-            const float valid = depth[i % P] > 0.f ? 1.f : 0.f;
+            const float valid = depth[i / C] > 0.f ? 1.f : 0.f;
             out[i] = valid * fabsf(__fmul_rn(OUT[3 * ld + m], trunc));
         }
     }
 };
 
-// mean over the pixels of one candidate (warp per candidate; fixed summation order)
-__global__ void ro_reduce_kernel(const float* __restrict__ vals, int c_count, int P, float sdf_weight,
-                                 float* __restrict__ fitness, float* __restrict__ mean_sdf) {
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (c >= c_count) return;
+// mean over the pixels of one candidate, vals[pixel][candidate].  A block owns 32 candidates: thread (cl = lane, slice = warp)
+// sums the pixels slice, slice + 32, ... (coalesced over the candidates), then the 32 slice sums are added in slice order:
+// a fixed summation order per candidate, independent of how the candidates are sharded.
+__global__ void __launch_bounds__(1024) ro_reduce_kernel(const float* __restrict__ vals, int c_count, int P, float sdf_weight,
+                                                         float* __restrict__ fitness, float* __restrict__ mean_sdf) {
+    __shared__ float part[32][33];
+    const int cl = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
     float s = 0.f;
-    for (int p = lane; p < P; p += 32) s += vals[(size_t)c * P + p];
-    s = warp_sum(s);
-    if (lane == 0) {
-        const float mean = s / (float)P;
+    if (c < c_count) {
+#pragma unroll 4
+        for (int p = slice; p < P; p += 32) s += vals[(size_t)p * c_count + c];
+    }
+    part[slice][cl] = s;
+    __syncthreads();
+    if (slice == 0 && c < c_count) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t += part[k][cl];
+        const float mean = t / (float)P;
         mean_sdf[c] = mean;
         fitness[c] = mean * sdf_weight;
     }
@@ -181,14 +194,14 @@ MF_API int mf_ro_score(const float* particles6, const float* search_size, const 
     FieldDev d; int rc = mf_field_to_dev(field, &d); if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     float* Rt = scratch;                                   // c_count * 12
-    float* vals = scratch + (size_t)c_count * 12;          // c_count * P
+    float* vals = scratch + (size_t)c_count * 12;          // P * c_count, pixel-major
     ro_pose_kernel<<<(c_count + 127) / 128, 128, 0, st>>>(particles6, search_size, rot_cur, trans_cur, c_begin, c_count, Rt, pst7);
     MF_LAUNCH_CHECK();
-    SrcRO src{Rt, dirs_cam, target_d, P};
-    EpiAbsSdf epi{vals, target_d, P, (float)trunc};
+    SrcRO src{Rt, dirs_cam, target_d, c_count};
+    EpiAbsSdf epi{vals, target_d, c_count, (float)trunc};
     rc = launch_field_fwd_auto<SrcRO, EpiAbsSdf, true>(d, src, epi, (int64_t)c_count * P, st, nullptr, false, 2);
     if (rc) return rc;
-    ro_reduce_kernel<<<(c_count + 7) / 8, 256, 0, st>>>(vals, c_count, P, (float)sdf_weight, fitness, mean_sdf);
+    ro_reduce_kernel<<<(c_count + 31) / 32, 1024, 0, st>>>(vals, c_count, P, (float)sdf_weight, fitness, mean_sdf);
     MF_LAUNCH_CHECK();
     return MF_OK;
 }

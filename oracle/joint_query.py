@@ -39,7 +39,9 @@ def compute_weights(entropy, dist_w, mask):                        # vis/math_he
 
 
 def joint_query(points, fields, first_kf_poses, aabb_min, aabb_max, centroids, vis_masks=None, color=False):
-    """points (G,3) fp32 world; per submap i: fields[i] (OracleField), first_kf_poses[i] (4,4) fp32
+    """points (G,3) world, float64 as the reference builds them (np.meshgrid of linspace axes, Mesher.py:43-55) or float32;
+    containment is tested on the coordinates as given (open3d works on float64, Mesher.py:470), the network sees them
+    rounded to float32 (Mesher.py:477).  per submap i: fields[i] (OracleField), first_kf_poses[i] (4,4) fp32
     c2w of the submap frame, aabb (3,) fp64, centroid (3,) fp32.  Returns dict with blended sdf
     (or rgb), per-submap containment masks (the integer 'submap assignment') and weights."""
     G, M = points.shape[0], len(fields)
@@ -49,7 +51,8 @@ def joint_query(points, fields, first_kf_poses, aabb_min, aabb_max, centroids, v
     tsdf = np.full((G, M), -1, np.float32)
     rgb = np.zeros((G, M, 3), np.float32)
     dist_w = np.zeros((G, M), np.float32)
-    p64 = points.astype(np.float64)
+    p64 = np.asarray(points, dtype=np.float64)
+    points = np.asarray(points).astype(np.float32)
     for i in range(M):
         c1 = np.all((p64 >= aabb_min[i]) & (p64 <= aabb_max[i]), axis=-1)           # Mesher.py:470
         contain[:, i] = c1
