@@ -57,7 +57,7 @@ constexpr int64_t SCR_CTA_WORDS = (int64_t)SCR_WORDS * TC_TP;
 constexpr int REGS_CHAIN = 160, REGS_WGRAD = 88, REGS_SCATTER = 104;       // 256 x 160 + 128 x 88 + 128 x 104 = 65,536
 constexpr int U_FEAT = 112;                            // U sits at features [112, 128) of the X staging tile
 // ---- mbarriers ----
-enum { B_MMA = 0, B_DG3, B_DCONS, B_FULL, B_DWRDY, B_TDONE, B_FREE0, B_COUNT = B_FREE0 + 4 };   // B_FREE0 + q: MMAs of staged quarter q done
+enum { B_MMA = 0, B_DG3, B_DCONS, B_DWFREE, B_DWRDY, B_FREE0, B_COUNT = B_FREE0 + 4 };   // B_FREE0 + q: MMAs of staged quarter q done
 constexpr int N_X3 = 112;                              // wgrad-3 X width: 64 sdf_emb + 32 grid + ones column + padding to 16
 
 __device__ __forceinline__ void chain_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CHAIN_NT) : "memory"); }
@@ -133,6 +133,29 @@ __device__ __forceinline__ void split32(const float (&v)[32], uint32_t (&hi)[16]
     for (int i = 0; i < 16; ++i) umma::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
 }
 
+// Staging stores with everything that depends on the thread folded into 8 precomputed shared-memory addresses:
+// P[j] = address of 16-byte chunk j of this thread's row in its 64-feature block (block h of a tile at offset 0, 128-byte
+// swizzle: chunk j sits at (j ^ (row & 7)) * 16); the tile and lo-part offsets are immediates -> one instruction per store.
+template <int OFF>
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c_, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0+%1], {%2, %3, %4, %5};" ::"r"(addr), "n"(OFF), "r"(a), "r"(b), "r"(c_), "r"(d) : "memory");
+}
+template <int TILE_OFF, int CC>                         // 32 features = half CC of the block: chunks 4 CC .. 4 CC + 3
+__device__ __forceinline__ void put32(const uint32_t (&P)[8], const uint32_t (&pk)[16]) {
+#pragma unroll
+    for (int c_ = 0; c_ < 4; ++c_) sts128<TILE_OFF>(P[4 * CC + c_], pk[4 * c_], pk[4 * c_ + 1], pk[4 * c_ + 2], pk[4 * c_ + 3]);
+}
+template <int TILE_OFF, int SG>                         // 16 features = slot group SG of the block: chunks 2 SG, 2 SG + 1
+__device__ __forceinline__ void put16(const uint32_t (&P)[8], const uint32_t (&pk)[8]) {
+#pragma unroll
+    for (int c_ = 0; c_ < 2; ++c_) sts128<TILE_OFF>(P[2 * SG + c_], pk[4 * c_], pk[4 * c_ + 1], pk[4 * c_ + 2], pk[4 * c_ + 3]);
+}
+template <int TILE_OFF>                                 // this thread's 64 features of a tile: hi words and lo words (2 blocks later)
+__device__ __forceinline__ void put64(const uint32_t (&P)[8], const uint32_t (&wh)[2][16], const uint32_t (&wl)[2][16]) {
+    put32<TILE_OFF, 0>(P, wh[0]); put32<TILE_OFF, 1>(P, wh[1]);
+    put32<TILE_OFF + 2 * (int)QBLK, 0>(P, wl[0]); put32<TILE_OFF + 2 * (int)QBLK, 1>(P, wl[1]);
+}
+
 // park / reload 32 packed words (hi 16 at word w0.., lo 16 at word 64 + w0.. of a 128-word region; 32 + w0.. for the 64-word
 // rgb_emb region) of this thread's point in the CTA scratch; L2 only (the same thread re-reads what it wrote)
 __device__ __forceinline__ void scr_store(uint32_t* scr_p, int region, int lo_off, int w0, const uint32_t (&hi)[16], const uint32_t (&lo)[16]) {
@@ -180,7 +203,7 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
     if (warp == 0) umma::tmem_alloc<512>(tmem_ptr);
     if (tid == 0) {
         umma::mbar_init(c.bars + B_MMA, 1); umma::mbar_init(c.bars + B_DG3, 1); umma::mbar_init(c.bars + B_DCONS, SC_NT);
-        umma::mbar_init(c.bars + B_FULL, 64); umma::mbar_init(c.bars + B_DWRDY, 1); umma::mbar_init(c.bars + B_TDONE, 1);
+        umma::mbar_init(c.bars + B_DWFREE, WG_NT); umma::mbar_init(c.bars + B_DWRDY, 1);
         for (int q = 0; q < 4; ++q) umma::mbar_init(c.bars + B_FREE0 + q, 1);
         umma::fence_barrier_init();
     }
@@ -194,20 +217,24 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
     const int64_t N = am.n(N_all);                     // active points only (ascending point indices in am.idx)
     const int64_t n_tiles = (N + TC_TP - 1) / TC_TP;
     const int p = tid & (TC_TP - 1);
-#define B2_MARK(slot) do { if (prof && blockIdx.x == 0 && k == 1 && (tid & 127) == 0) prof[slot] = clock64(); } while (0)
+#define B2_MARK(slot) do { if (prof && blockIdx.x == 0 && k == 1 && (ctid & 127) == 0) prof[slot] = clock64(); } while (0)
 
-    if (tid < CHAIN_NT) {
+    // Role order SCATTER (warps 0-3), CHAIN (4-11), WGRAD (12-15): the warp scheduler prefers the highest eligible warp id.
+    // The MMA issuer must react at once to a staged quarter (measured: 1.4-1.8 k cycles late when it sat below the chain's
+    // warps), the chain's instructions are latency critical, the reductions of SCATTER are throughput work.
+    const int ctid = tid - SC_NT;                      // thread index inside the chain (outside [0, 256) for the other roles)
+    if (ctid >= 0 && ctid < CHAIN_NT) {
         // =============================== CHAIN ===============================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CHAIN));
-        const int h = tid >> 7;
+        const int h = ctid >> 7;
         uint32_t ph_mma = 0;
         uint32_t k = 0;
         auto round = [&](auto issue) {                 // publish TMEM stores, rendezvous, thread 0 issues + commits, all wait
             umma::wait_st();
             umma::fence_before_sync();
             chain_sync();
-            if (tid == 0) { umma::fence_after_sync(); issue(); umma::commit(c.bars + B_MMA); }
-            c.ok &= umma::mbar_wait(c.bars + B_MMA, ph_mma);
+            if (ctid == 0) { umma::fence_after_sync(); issue(); umma::commit(c.bars + B_MMA); }
+            c.ok &= umma::mbar_wait_spin(c.bars + B_MMA, ph_mma);
             ph_mma ^= 1;
             umma::fence_after_sync();
         };
@@ -216,11 +243,46 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
         // never more than one phase behind).  lay = global layer counter (3 per tile).
         const int row = p & (QROWS - 1), quarter = p >> 5;
         auto stage_wait = [&](uint32_t lay) {
-            c.ok &= umma::mbar_wait(c.bars + B_FREE0 + ((quarter + 3) & 3), quarter == 0 ? ((lay + 1u) & 1u) : (lay & 1u));
+            c.ok &= umma::mbar_wait_spin(c.bars + B_FREE0 + ((quarter + 3) & 3), quarter == 0 ? ((lay + 1u) & 1u) : (lay & 1u));
         };
-        auto stage_done = [&]() { umma::fence_proxy_async(); umma::mbar_arrive(c.bars + B_FULL); };
-        uint8_t *z_hi = c.base + S_ZS, *z_lo = z_hi + 2 * QBLK, *x_hi = c.base + S_XS, *x_lo = x_hi + 2 * QBLK;
-        uint8_t *h_hi = c.base + S_HS, *h_lo = h_hi + 2 * QBLK;
+        // After the two warps of a quarter have written their rows (and made them visible to the tensor core), one thread of
+        // the quarter issues the quarter's MMAs itself -- no hop through another warp -- and commits `free`; the last quarter of a
+        // layer also commits `dw_ready` for WGRAD's read-out.  L: 0 = layer 3 (dWs1 + dbs1 = dZ3^T x3, H3^T U), 1 = layer 2
+        // (dW2 = dH^T H1), 2 = layer 1 (dW1 + db1 = dZ1^T e, [e | rgb_emb]^T U).  Passes (A hi, B hi), (A lo, B hi), (A hi, B lo)
+        // over two 16-point k-steps; lo tiles follow 2 blocks later; descriptors differ by constants in the start-address field.
+        constexpr int U_BYTE = (U_FEAT - 64) * 2;      // U inside the second 64-feature block of the X tile
+        const uint64_t dz0 = umma::desc_mn(c.base + S_ZS, 0, QBLK), dx0 = umma::desc_mn(c.base + S_XS, 0, QBLK);
+        const uint64_t dh0 = umma::desc_mn(c.base + S_HS, 0, QBLK), du0 = umma::desc_mn(c.base + S_XS + QBLK + U_BYTE, 0, QBLK);
+        constexpr uint32_t LO_STEP = (2 * QBLK) >> 4, KS_STEP = (16 * 128) >> 4;
+        auto stage_done = [&](int L, uint32_t lay) {
+            umma::fence_proxy_async();
+            asm volatile("bar.sync %0, 64;" ::"r"(3 + quarter) : "memory");
+            if (h == 0 && (tid & 31) == 0) {
+                umma::fence_after_sync();
+                if (quarter == 0) c.ok &= umma::mbar_wait_spin(c.bars + B_DWFREE, (lay + 1u) & 1u);   // DW of the previous layer read out
+                const uint32_t idesc_w = umma::idesc_bf16(128, L == 0 ? N_X3 : (L == 1 ? D_H : 64), 1, 1);
+                constexpr uint32_t idesc_u = umma::idesc_bf16(128, 16, 1, 1);
+                const uint32_t col_u = c.tmem + (uint32_t)(T_DW + (L == 0 ? N_X3 : 64));
+                const uint64_t db = L == 2 ? dh0 : dx0;                      // B of the wide product: X (layers 3, 2) or e = first block of HS
+                const uint32_t acc0 = quarter == 0 ? 0u : 1u;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const int pass = j >> 1, ks = j & 1;
+                    umma::mma_ss(c.tmem + T_DW, dz0 + (uint64_t)((pass == 1 ? LO_STEP : 0) + ks * KS_STEP),
+                                 db + (uint64_t)((pass == 2 ? LO_STEP : 0) + ks * KS_STEP), idesc_w, j == 0 ? acc0 : 1u);
+                }
+                if (L != 1) {
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        const int pass = j >> 1, ks = j & 1;
+                        umma::mma_ss(col_u, dh0 + (uint64_t)((pass == 1 ? LO_STEP : 0) + ks * KS_STEP),
+                                     du0 + (uint64_t)((pass == 2 ? LO_STEP : 0) + ks * KS_STEP), idesc_u, j == 0 ? acc0 : 1u);
+                    }
+                }
+                umma::commit(c.bars + B_FREE0 + quarter);
+                if (quarter == 3) umma::commit(c.bars + B_DWRDY);
+            }
+        };
         uint32_t* scr_p = scratch + (size_t)blockIdx.x * SCR_CTA_WORDS + p;
         // copy this thread's 64 dZ features (two 32-feature groups) from an operand region into the Z staging tile
         // this thread's 64 dZ features (two 32-feature groups) of an operand region: load (one TMEM round trip) / store to ZS
@@ -232,10 +294,10 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
             }
             umma::wait_ld();
         };
-        auto store_z = [&](const uint32_t (&wh)[2][16], const uint32_t (&wl)[2][16]) {
+        uint32_t P[8];                                 // chunk addresses of this thread's row in block h (see sts128)
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) { umma::store_row32(z_hi, row, 2 * h + cc, wh[cc], QBLK); umma::store_row32(z_lo, row, 2 * h + cc, wl[cc], QBLK); }
-        };
+        for (int j = 0; j < 8; ++j)
+            P[j] = umma::smem_u32(c.base) + (uint32_t)h * QBLK + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128) + (uint32_t)(((j ^ row) & 7) << 4);
 
         int64_t i_next = 0;
         { const int64_t s0 = (int64_t)blockIdx.x * TC_TP + p; if (s0 < N) i_next = am(s0); }
@@ -244,6 +306,8 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
             const bool valid = slot < N;
             const int64_t i = i_next;                                       // (loaded one tile ahead)
             { const int64_t s1 = slot + (int64_t)gridDim.x * TC_TP; i_next = s1 < N ? am(s1) : 0; }
+            // (prefetching the next tile's cached operand words into L2 here shortened the load phase by 2 k cycles but cost more in
+            // load / store unit traffic than it saved: 0.287 vs 0.273 ms)
             const uint32_t lay0 = 3u * k;                                   // global layer counter of this tile's first wgrad
             B2_MARK(0);
             float g[3], gs[7];                                 // d loss / d (rgb 3 | sdf, entropy, prob[5])
@@ -440,7 +504,7 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
             umma::wait_st();
             umma::fence_before_sync();
             chain_sync();
-            if (tid == 0) {
+            if (ctid == 0) {
                 umma::fence_after_sync();
                 issue_dgrad(c, T_R1_HI, T_R1_LO, IMG_W3_HI, IMG_W3_LO, D_SDF_IN);
                 umma::commit(c.bars + B_DG3);
@@ -455,9 +519,9 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
                 if (prof && blockIdx.x == 0 && k == 1 && (tid & 31) == 0 && h == 0) prof[32 + 4 * quarter] = clock64();
                 stage_wait(lay0);
                 if (prof && blockIdx.x == 0 && k == 1 && (tid & 31) == 0 && h == 0) prof[33 + 4 * quarter] = clock64();
-                store_z(zh, zl);
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) { umma::store_row32(h_hi, row, 2 * h + cc, ah[cc], QBLK); umma::store_row32(h_lo, row, 2 * h + cc, al[cc], QBLK); }
+                if (prof && blockIdx.x == 0 && k == 1 && (tid & 31) == 0 && h == 1) prof[60 + quarter] = clock64();
+                put64<S_ZS>(P, zh, zl);
+                put64<S_HS>(P, ah, al);
                 // x3 words of this thread (reuse zh / zl): h = 0 sdf_emb (64 features), h = 1 grid (32) + [1 | 0.. | U]
                 if (h == 0) {
 #pragma unroll
@@ -465,8 +529,7 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
                         umma::tmem_ld16(c.lane_base + T_R2_HI + 16 * cc, zh[cc]); umma::tmem_ld16(c.lane_base + T_R2_LO + 16 * cc, zl[cc]);
                     }
                     umma::wait_ld();
-#pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) { umma::store_row32(x_hi, row, cc, zh[cc], QBLK); umma::store_row32(x_lo, row, cc, zl[cc], QBLK); }
+                    put64<S_XS>(P, zh, zl);
                 } else {
                     umma::tmem_ld16(c.lane_base + T_G_HI, zh[0]); umma::tmem_ld16(c.lane_base + T_G_LO, zl[0]);
 #pragma unroll
@@ -475,15 +538,15 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
 #pragma unroll
                     for (int t = 0; t < 4; ++t) { zh[1][8 + t] = uh[t]; zl[1][8 + t] = ul[t]; }  // features 112 .. 119 = U
                     umma::wait_ld();
-#pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) { umma::store_row32(x_hi, row, 2 + cc, zh[cc], QBLK); umma::store_row32(x_lo, row, 2 + cc, zl[cc], QBLK); }
+                    put64<S_XS>(P, zh, zl);
                 }
                 if (prof && blockIdx.x == 0 && k == 1 && (tid & 31) == 0 && h == 0) prof[34 + 4 * quarter] = clock64();
-                stage_done();
+                stage_done(0, lay0);
                 if (prof && blockIdx.x == 0 && k == 1 && (tid & 31) == 0 && h == 0) prof[35 + 4 * quarter] = clock64();
+                if (prof && blockIdx.x == 0 && k == 1 && (tid & 31) == 0 && h == 1) prof[56 + quarter] = clock64();
             }
             B2_MARK(6);
-            c.ok &= umma::mbar_wait(c.bars + B_DG3, k & 1u);
+            c.ok &= umma::mbar_wait_spin(c.bars + B_DG3, k & 1u);
             umma::fence_after_sync();
             B2_MARK(7);
             // ---- dH = [d sdf_emb (dgrad of layer 3), d rgb_emb (colour head)] -> R2 (this thread's x3 words are staged) ----
@@ -505,8 +568,8 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
             umma::wait_st();
             umma::fence_before_sync();
             chain_sync();
-            if (tid == 0) {
-                c.ok &= umma::mbar_wait(c.bars + B_DCONS, k & 1u);
+            if (ctid == 0) {
+                c.ok &= umma::mbar_wait_spin(c.bars + B_DCONS, k & 1u);
                 umma::fence_after_sync();
                 issue_dgrad(c, T_R2_HI, T_R2_LO, IMG_W2_HI, IMG_W2_LO, D_H);
                 umma::commit(c.bars + B_MMA);
@@ -519,12 +582,11 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
                 for (int cc = 0; cc < 2; ++cc) scr_load(scr_p, SCR_H1, 64, 32 * h + 16 * cc, ah[cc], al[cc]);
                 load_z(T_R2_HI, T_R2_LO, zh, zl);
                 stage_wait(lay0 + 1u);
-                store_z(zh, zl);
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) { umma::store_row32(x_hi, row, 2 * h + cc, ah[cc], QBLK); umma::store_row32(x_lo, row, 2 * h + cc, al[cc], QBLK); }
-                stage_done();
+                put64<S_ZS>(P, zh, zl);
+                put64<S_XS>(P, ah, al);
+                stage_done(1, lay0 + 1u);
             }
-            c.ok &= umma::mbar_wait(c.bars + B_MMA, ph_mma);
+            c.ok &= umma::mbar_wait_spin(c.bars + B_MMA, ph_mma);
             ph_mma ^= 1;
             umma::fence_after_sync();
             B2_MARK(9);
@@ -551,78 +613,40 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
                     for (int qq = 0; qq < 4; ++qq) e_words(qq, eh[qq], el[qq]);
                     eh[0][7] = (eh[0][7] & 0x0000ffffu) | 0x3F800000u; el[0][7] &= 0x0000ffffu;  // slot 15 = 1.0: bias column / row
                     stage_wait(lay0 + 2u);
-                    store_z(zh, zl);
-#pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) { umma::store_row16(h_hi, row, qq, eh[qq]); umma::store_row16(h_lo, row, qq, el[qq]); }
+                    put64<S_ZS>(P, zh, zl);
+                    put16<S_HS, 0>(P, eh[0]); put16<S_HS, 1>(P, eh[1]); put16<S_HS, 2>(P, eh[2]); put16<S_HS, 3>(P, eh[3]);
+                    put16<S_HS + 2 * (int)QBLK, 0>(P, el[0]); put16<S_HS + 2 * (int)QBLK, 1>(P, el[1]);
+                    put16<S_HS + 2 * (int)QBLK, 2>(P, el[2]); put16<S_HS + 2 * (int)QBLK, 3>(P, el[3]);
                 } else {
                     uint32_t ah[2][16], al[2][16];
 #pragma unroll
                     for (int cc = 0; cc < 2; ++cc) scr_load(scr_p, SCR_RGB, 32, 16 * cc, ah[cc], al[cc]);
                     stage_wait(lay0 + 2u);
-                    store_z(zh, zl);
-#pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) { umma::store_row32(h_hi, row, 2 + cc, ah[cc], QBLK); umma::store_row32(h_lo, row, 2 + cc, al[cc], QBLK); }
+                    put64<S_ZS>(P, zh, zl);
+                    put64<S_HS>(P, ah, al);
 #pragma unroll
                     for (int t = 0; t < 16; ++t) { ah[0][t] = 0u; al[0][t] = 0u; }
 #pragma unroll
                     for (int t = 0; t < 4; ++t) { ah[0][8 + t] = uh[t]; al[0][8 + t] = ul[t]; }
-                    umma::store_row32(x_hi, row, 3, ah[0], QBLK); umma::store_row32(x_lo, row, 3, al[0], QBLK);
+                    put32<S_XS, 1>(P, ah[0]); put32<S_XS + 2 * (int)QBLK, 1>(P, al[0]);
                 }
             }
-            stage_done();
+            stage_done(2, lay0 + 2u);
             B2_MARK(10);
             umma::fence_before_sync();
             chain_sync();          // every accumulator / operand read of this tile is done before the next tile's stores
         }
-    } else if (tid < CHAIN_NT + WG_NT) {
+    } else if (ctid >= CHAIN_NT) {
         // =============================== WGRAD ===============================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_WGRAD));
-        const int wt = tid - CHAIN_NT;                 // = accumulator lane n
+        const int wt = ctid - CHAIN_NT;                // = accumulator lane n
         // destination of this lane's row of the colour-head product [e | rgb_emb]^T U inside rgb_linear.0.weight (or -1)
         const int kin = wt >= 64 ? wt - 64 : (tc_e_slot_to_index(wt) >= 0 ? 64 + tc_e_slot_to_index(wt) : -1);
-        constexpr int U_BYTE = (U_FEAT - 64) * 2;      // U inside the second 64-feature block of the X tile
-        // MMAs of a staged quarter:  L = 0: dWs1 (+ dbs1) = dZ3^T x3,  H3^T U;   L = 1: dW2 = dH^T H1;
-        //                            L = 2: dW1 (+ db1) = dZ1^T e,  [e | rgb_emb]^T U.
-        // Descriptors of the (hi tile, k-step 0) operands; the others differ by constants in the start-address field (>> 4).
-        const uint64_t dz0 = umma::desc_mn(c.base + S_ZS, 0, QBLK), dx0 = umma::desc_mn(c.base + S_XS, 0, QBLK);
-        const uint64_t dh0 = umma::desc_mn(c.base + S_HS, 0, QBLK), du0 = umma::desc_mn(c.base + S_XS + QBLK + U_BYTE, 0, QBLK);
-        constexpr uint32_t LO_STEP = (2 * QBLK) >> 4, KS_STEP = (16 * 128) >> 4;
-        uint32_t k = 0, ho = 0, lay = 0;
+        uint32_t k = 0, lay = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
 #pragma unroll 1
             for (int L = 0; L < 3; ++L, ++lay) {
-                if (wt == 0) {
-                    const uint32_t idesc_w = umma::idesc_bf16(128, L == 0 ? N_X3 : (L == 1 ? D_H : 64), 1, 1);
-                    constexpr uint32_t idesc_u = umma::idesc_bf16(128, 16, 1, 1);
-                    const uint32_t col_u = c.tmem + (uint32_t)(T_DW + (L == 0 ? N_X3 : 64));
-                    const uint64_t db = L == 2 ? dh0 : dx0;                  // B of the wide product: X (layers 3, 2) or e = first block of HS
-#pragma unroll 1
-                    for (int q = 0; q < 4; ++q, ++ho) {
-                        c.ok &= umma::mbar_wait(c.bars + B_FULL, ho & 1u);
-                        umma::fence_after_sync();
-                        if (prof && blockIdx.x == 0 && k == 1 && L == 0) prof[48 + 2 * q] = clock64();
-                        const uint32_t acc0 = q == 0 ? 0u : 1u;
-                        // passes (A hi, B hi), (A lo, B hi), (A hi, B lo); two 16-point k-steps each; lo tiles follow 2 blocks later
-#pragma unroll
-                        for (int j = 0; j < 6; ++j) {
-                            const int pass = j >> 1, ks = j & 1;
-                            umma::mma_ss(c.tmem + T_DW, dz0 + (uint64_t)((pass == 1 ? LO_STEP : 0) + ks * KS_STEP),
-                                         db + (uint64_t)((pass == 2 ? LO_STEP : 0) + ks * KS_STEP), idesc_w, j == 0 ? acc0 : 1u);
-                        }
-                        if (L != 1) {
-#pragma unroll
-                            for (int j = 0; j < 6; ++j) {
-                                const int pass = j >> 1, ks = j & 1;
-                                umma::mma_ss(col_u, dh0 + (uint64_t)((pass == 1 ? LO_STEP : 0) + ks * KS_STEP),
-                                             du0 + (uint64_t)((pass == 2 ? LO_STEP : 0) + ks * KS_STEP), idesc_u, j == 0 ? acc0 : 1u);
-                            }
-                        }
-                        umma::commit(c.bars + B_FREE0 + q);
-                        if (prof && blockIdx.x == 0 && k == 1 && L == 0) prof[49 + 2 * q] = clock64();
-                    }
-                    umma::commit(c.bars + B_DWRDY);
-                }
-                c.ok &= umma::mbar_wait(c.bars + B_DWRDY, lay & 1u);
+                c.ok &= umma::mbar_wait_spin(c.bars + B_DWRDY, lay & 1u);
                 umma::fence_after_sync();
                 if (prof && blockIdx.x == 0 && k == 1 && wt == 0) prof[16 + L] = clock64();
                 // read-out: lane n owns DW[n][*]; every element has one owner thread: reductions without return
@@ -662,7 +686,7 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
                 }
                 if (prof && blockIdx.x == 0 && k == 1 && wt == 0) prof[20 + L] = clock64();
                 umma::fence_before_sync();
-                wg_sync();                               // DW fully read before the next layer's first MMA overwrites it
+                umma::mbar_arrive(c.bars + B_DWFREE);    // DW fully read: the next layer's first MMA may overwrite it
             }
         }
     } else {
@@ -675,7 +699,7 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
             const int64_t i = valid ? am(slot) : 0;
             float x[3] = {0.f, 0.f, 0.f};
             if (valid) src.point(i, f, x);
-            c.ok &= umma::mbar_wait(c.bars + B_DG3, k & 1u);
+            c.ok &= umma::mbar_wait_spin(c.bars + B_DG3, k & 1u);
             umma::fence_after_sync();
             if (prof && blockIdx.x == 0 && k == 1 && p == 0) prof[24] = clock64();
             uint32_t r[32];
@@ -687,6 +711,7 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
             // hand-offs for the load / store unit -- was measured slower: 0.312 vs 0.291 ms; the forward phases of the next tile
             // use the unit just as much)
             if (prof && blockIdx.x == 0 && k == 1 && p == 0) prof[26] = clock64();
+#ifndef MF_EXP_NOSCATTER
             if (valid) {
                 float dx[3];
 #pragma unroll 1
@@ -700,6 +725,7 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
                         grid_level_bwd<false>(x, make_float2(dy8[2 * ll], dy8[2 * ll + 1]), nullptr, grad_grid, level_info(f, gq * 4 + ll), dx);
                 }
             }
+#endif
             if (prof && blockIdx.x == 0 && k == 1 && p == 0) prof[25] = clock64();
         }
     }

@@ -32,6 +32,24 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     return false;
 }
 
+// Polling variant: mbarrier.test_wait never suspends the thread.  try_wait puts the thread to sleep and (measured on B200,
+// scripts/prof_bwd2.py) the wake-up after the phase completes came 1-2.5 k cycles late on the hand-off critical paths.
+__device__ __forceinline__ bool mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t it = 0; it < (1u << 26); ++it) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }

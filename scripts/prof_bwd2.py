@@ -38,6 +38,4 @@ print(f"scatter: dgrad3 seen at +{t[24]-t[0]:d}, released at +{t[26]-t[0]:d}, re
 print("hand-off 3, per quarter (h = 0 warp): [regs ready, buffer free, stores done, fence+arrive done] relative to tile start")
 for q in range(4):
     print("  q%d" % q, [t[32 + 4 * q + j] - t[0] for j in range(4)])
-print("WGRAD layer 3 per quarter: [full seen, MMAs issued + committed]")
-for q in range(4):
-    print("  q%d" % q, [t[48 + 2 * q + j] - t[0] for j in range(2)])
+print("h = 1 warp: [buffer free seen, arrived]", [[t[60 + q] - t[0], t[56 + q] - t[0]] for q in range(4)])
