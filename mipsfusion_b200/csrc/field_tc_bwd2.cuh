@@ -1,24 +1,31 @@
 // Tensor-core (tcgen05) backward of the fused field evaluation, role-split version (the default; field_tc_bwd.cuh keeps
 // the single-role kernel for A/B and for the pose-gradient route).  One persistent CTA per SM, 16 warps, 128 points per tile:
 //
-//   warps 0-7   CHAIN    the serial dependency chain of a tile: reload the encoded operand words (feature cache), forward
+//   warps 4-11  CHAIN    the serial dependency chain of a tile: reload the encoded operand words (feature cache), forward
 //                        layers 1-3, heads (softmax forward / backward), dZ3, dgrad3, dH, dgrad2, dZ1.  Two threads per point
 //                        (64 features each).  After each layer's dZ is in tensor memory (and its dgrad is issued) the two
-//                        warps that own a 32-point quarter copy the wgrad operands of that quarter -- bf16 hi / lo
-//                        [point][feature] rows -- into the staging buffers in shared memory and hand them to WGRAD.
-//   warps 8-11  WGRAD    waits for a staged quarter, issues its MMAs (both operands MN-major from shared memory, bf16x3):
+//                        warps that own a 32-point quarter copy the operands of that quarter's wgrad products -- bf16 hi / lo
+//                        [point][feature] rows -- into one of two staging buffers in shared memory (quarter q uses buffer
+//                        q & 1: quarters 0 / 1 and 2 / 3 fill in parallel, a buffer is refilled while the MMAs of the other one
+//                        run) and issue the quarter's MMAs themselves (both operands MN-major from shared memory, bf16x3):
 //                          dW[n][k] += sum_p dZ[p][n] X[p][k]                       (the three 128-wide layers)
 //                          dV[n][c] += sum_p A[p][n] U[p][c],  U = [dlogits 5 | dRGB 3 | 0..]   (the two narrow heads:
 //                             A = H3 gives sdf_linear.2.weight; A = [e | rgb_emb] gives rgb_linear.0.weight; the ones
-//                             column of e gives both head biases) -- no warp-shuffle reductions over points anywhere,
-//                        and after the fourth quarter of a layer reads the result from tensor memory and adds it to the CTA's
-//                        partial gradient (coalesced reductions).
-//   warps 12-15 SCATTER  one thread per point: takes d(grid features) of the tile straight from the dgrad3 accumulator and
+//                             column of e gives both head biases) -- no warp-shuffle reductions over points anywhere.
+//   warps 12-15 WGRAD    after the last quarter of a layer reads the 128 x K result from tensor memory and adds it to the CTA's
+//                        partial gradient (coalesced reductions; every element has one owner thread).
+//   warps 0-3   SCATTER  one thread per point: takes d(grid features) of the tile straight from the dgrad3 accumulator and
 //                        scatters it into the hash-table gradient (128 reductions per point; the reduction rate of the SM is
 //                        the bound of this stage, it no longer blocks the warps that feed the tensor core).
+// (role order by warp id: the scheduler prefers the highest eligible warp id; the reductions are throughput work.)
 //
 // WGRAD's read-out and SCATTER's reductions of tile k run while the chain is already in tile k+1.  Hand-offs are mbarriers
-// only (full / free per staged quarter, dw_ready per layer, dg3 / dcons around the accumulator columns SCATTER reads).
+// only (free / iss per staged quarter, dw_ready / dw_free per layer, dg3 / dcons around the accumulator columns SCATTER reads,
+// w1 for the TMA copy below).
+//
+// Shared memory: W2 | W3 images resident (128 KB) | two 32 KB staging buffers | fp32 section | logit partials.  The W1 image
+// (32 KB) lives in staging buffer 0 only while it is needed (forward layer 1): a TMA bulk copy (cp.async.bulk, async proxy)
+// brings it in at the start of every tile, after the last wgrad MMAs that read the buffer have completed.
 //
 // Bias gradients cost nothing per point: pts_linear.0.bias and sdf_linear.0.bias are a ones column appended to the wgrad X
 // operand (layer-1 slot 15, layer-3 feature 96), pts_linear.2.bias is linear in the other gradients
@@ -27,7 +34,12 @@
 // Tensor memory: D [0,128) chain accumulator | R1 [128,256) e, H1, dZ3, dZ1 (hi, lo) | R2 [256,384) x3 = [sdf_emb | grid],
 //                dH (hi, lo) | DW [384,512) wgrad accumulator.
 // Activations that a later wgrad needs but tensor memory has no room for (H1, H3, rgb_emb: bf16 hi / lo words) are parked in
-// a CTA-private scratch in global memory (L2 resident, [word][point], written and re-read by the same thread).
+// a CTA-private scratch in global memory (L2 resident, [word][point]).
+//
+// Measured on B200 at C1 (98.7 k active of 176 k points; scripts/prof_bwd2.py): 0.265 ms vs 0.300 ms for the single-role
+// kernel.  What the time is: the chain's own work is ~40 k cycles per tile, the five staged products add ~30 k (per product:
+// stores 0.7 k, fence + quarter barrier + issue 1-1.8 k, MMA -> free 0.9 k, twice), and every load / store unit operation of
+// the chain queues behind SCATTER's reductions (without them the kernel takes 0.24 ms).
 #pragma once
 #include "field_tc_bwd.cuh"
 
@@ -37,15 +49,16 @@ constexpr int B2_NT = 512, CHAIN_NT = 256, WG_NT = 128, SC_NT = 128;
 constexpr int QROWS = 32;                              // points per staged quarter tile
 constexpr uint32_t QBLK = QROWS * 128;                 // one 64-feature block of a quarter tile (4 KB)
 // ---- shared memory map ----
-constexpr int S_W = 0;                                 // weight image bytes [0, IMG_F32): W1 | W2 | W3, each hi then lo
-constexpr int S_ZS = IMG_F32;                          // dZ quarter: hi (2 blocks), lo (2 blocks) = 16 KB
-constexpr int S_XS = S_ZS + 4 * (int)QBLK;             // X quarter: 16 KB (features 112..127 of its second block carry U)
-constexpr int S_HS = S_XS + 4 * (int)QBLK;             // second A operand of a hand-off: H3 (layer 3) / [e | rgb_emb] (layer 1)
-constexpr int S_F32 = S_HS + 4 * (int)QBLK;            // fp32 section of the image
+constexpr int S_W = 0;                                 // weight image bytes [IMG_W2_HI, IMG_F32): W2 | W3, each hi then lo (128 KB)
+constexpr int W2H = 0, W2L = IMG_W2_LO - IMG_W2_HI, W3H = IMG_W3_HI - IMG_W2_HI, W3L = IMG_W3_LO - IMG_W2_HI;
+constexpr int S_ST = IMG_F32 - IMG_W2_HI;              // two staging buffers of 32 KB: A tile (hi 2 blocks, lo 2 blocks) | B tile
+constexpr int ST_A = 0, ST_B = 4 * (int)QBLK, ST_BYTES = 8 * (int)QBLK;
+constexpr int W1H = S_ST + IMG_W1_HI, W1L = S_ST + IMG_W1_LO;   // buffer 0 holds the W1 image during the forward layers (TMA, per tile)
+constexpr int S_F32 = S_ST + 2 * ST_BYTES;             // fp32 section of the image
 constexpr int S_PART = S_F32 + ((F_COUNT * 4 + 127) / 128) * 128;
 constexpr int PART_ROWS = 10;                          // logit partial sums: 2 halves x 5 classes
 constexpr int S_BAR = S_PART + PART_ROWS * TC_LD * 4;
-constexpr int S_BYTES = S_BAR + 128;
+constexpr int S_BYTES = S_BAR + 256;
 constexpr size_t SMEM = S_BYTES + 1024;
 static_assert(SMEM <= 227 * 1024, "shared memory budget");
 // ---- tensor memory map ----
@@ -55,9 +68,8 @@ constexpr int T_G_HI = T_R2_HI + 32, T_G_LO = T_R2_LO + 32;
 constexpr int SCR_H1 = 0, SCR_H3 = 128, SCR_RGB = 256, SCR_WORDS = 320;      // hi words first, then lo words, per region
 constexpr int64_t SCR_CTA_WORDS = (int64_t)SCR_WORDS * TC_TP;
 constexpr int REGS_CHAIN = 160, REGS_WGRAD = 88, REGS_SCATTER = 104;       // 256 x 160 + 128 x 88 + 128 x 104 = 65,536
-constexpr int U_FEAT = 112;                            // U sits at features [112, 128) of the X staging tile
 // ---- mbarriers ----
-enum { B_MMA = 0, B_DG3, B_DCONS, B_DWFREE, B_DWRDY, B_FREE0, B_COUNT = B_FREE0 + 4 };   // B_FREE0 + q: MMAs of staged quarter q done
+enum { B_MMA = 0, B_DG3, B_DCONS, B_DWFREE, B_DWRDY, B_W1, B_FREE0, B_ISS0 = B_FREE0 + 4, B_COUNT = B_ISS0 + 4 };   // B_FREE0 + q: MMAs of staged quarter q done
 constexpr int N_X3 = 112;                              // wgrad-3 X width: 64 sdf_emb + 32 grid + ones column + padding to 16
 
 __device__ __forceinline__ void chain_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CHAIN_NT) : "memory"); }
@@ -195,16 +207,16 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
     c.base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     c.fw = (const float*)(c.base + S_F32); c.part = (float*)(c.base + S_PART); c.bars = (uint64_t*)(c.base + S_BAR);
     uint32_t* tmem_ptr = (uint32_t*)(c.base + S_BAR + 8 * B_COUNT);
-    for (int i = tid; i < IMG_F32 / 16; i += B2_NT)
-        reinterpret_cast<uint4*>(c.base + S_W)[i] = __ldg(reinterpret_cast<const uint4*>(f.tc_img) + i);
+    for (int i = tid; i < (IMG_F32 - IMG_W2_HI) / 16; i += B2_NT)
+        reinterpret_cast<uint4*>(c.base + S_W)[i] = __ldg(reinterpret_cast<const uint4*>(f.tc_img + IMG_W2_HI) + i);
     for (int i = tid; i < F_COUNT * 4 / 16; i += B2_NT)
         reinterpret_cast<uint4*>(c.base + S_F32)[i] = __ldg(reinterpret_cast<const uint4*>(f.tc_img + IMG_F32) + i);
     umma::fence_proxy_async();
     if (warp == 0) umma::tmem_alloc<512>(tmem_ptr);
     if (tid == 0) {
         umma::mbar_init(c.bars + B_MMA, 1); umma::mbar_init(c.bars + B_DG3, 1); umma::mbar_init(c.bars + B_DCONS, SC_NT);
-        umma::mbar_init(c.bars + B_DWFREE, WG_NT); umma::mbar_init(c.bars + B_DWRDY, 1);
-        for (int q = 0; q < 4; ++q) umma::mbar_init(c.bars + B_FREE0 + q, 1);
+        umma::mbar_init(c.bars + B_DWFREE, WG_NT); umma::mbar_init(c.bars + B_DWRDY, 4); umma::mbar_init(c.bars + B_W1, 1);
+        for (int q = 0; q < 4; ++q) { umma::mbar_init(c.bars + B_FREE0 + q, 1); umma::mbar_init(c.bars + B_ISS0 + q, 1); }
         umma::fence_barrier_init();
     }
     umma::fence_before_sync();
@@ -238,50 +250,67 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
             ph_mma ^= 1;
             umma::fence_after_sync();
         };
-        // The single set of staging buffers is free once the MMAs of the previous hand-off have completed: quarter q - 1 of the
-        // same layer, or quarter 3 of the previous layer (one mbarrier per quarter, one completion per layer: a parity wait is
-        // never more than one phase behind).  lay = global layer counter (3 per tile).
-        const int row = p & (QROWS - 1), quarter = p >> 5;
-        auto stage_wait = [&](uint32_t lay) {
-            c.ok &= umma::mbar_wait_spin(c.bars + B_FREE0 + ((quarter + 3) & 3), quarter == 0 ? ((lay + 1u) & 1u) : (lay & 1u));
-        };
-        // After the two warps of a quarter have written their rows (and made them visible to the tensor core), one thread of
-        // the quarter issues the quarter's MMAs itself -- no hop through another warp -- and commits `free`; the last quarter of a
-        // layer also commits `dw_ready` for WGRAD's read-out.  L: 0 = layer 3 (dWs1 + dbs1 = dZ3^T x3, H3^T U), 1 = layer 2
-        // (dW2 = dH^T H1), 2 = layer 1 (dW1 + db1 = dZ1^T e, [e | rgb_emb]^T U).  Passes (A hi, B hi), (A lo, B hi), (A hi, B lo)
-        // over two 16-point k-steps; lo tiles follow 2 blocks later; descriptors differ by constants in the start-address field.
-        constexpr int U_BYTE = (U_FEAT - 64) * 2;      // U inside the second 64-feature block of the X tile
-        const uint64_t dz0 = umma::desc_mn(c.base + S_ZS, 0, QBLK), dx0 = umma::desc_mn(c.base + S_XS, 0, QBLK);
-        const uint64_t dh0 = umma::desc_mn(c.base + S_HS, 0, QBLK), du0 = umma::desc_mn(c.base + S_XS + QBLK + U_BYTE, 0, QBLK);
+        // ---- wgrad products: 5 per tile, each streamed in 4 quarters (the 32 points of a lane quadrant) through the staging
+        // buffer quarter & 1.  prod = global product counter (5 k + P):
+        //   P = 0  dWs1 (+ dbs1) = dZ3^T [sdf_emb | grid | 1]    -> DW[0, 112)      P = 1  dWs2 = H3^T U              -> DW[112, 128)
+        //   P = 2  dW2 = dH^T H1                                 -> DW[0, 128)
+        //   P = 3  dW1 (+ db1) = dZ1^T e (ones in slot 15)       -> DW[0, 64)       P = 4  [e | rgb_emb]^T U -> DW[64, 80)
+        // A buffer is free once the MMAs of the quarter that used it before have completed (`free`, one completion per product
+        // and quarter).  The two warps of a quarter write their rows, make them visible to the tensor core, and lane 0 of the
+        // h = 0 warp issues the quarter's MMAs: passes (A hi, B hi), (A lo, B hi), (A hi, B lo) over two 16-point k-steps.  The
+        // issue order q0 < q1 < q2 < q3 is enforced (`iss`): deterministic accumulation order, and q0's first MMA overwrites.
+        const int row = p & (QROWS - 1), quarter = p >> 5, lane = tid & 31;
+        uint32_t PA[8], PH[8], PQ[4];                  // chunk addresses of this thread's row: block 0 / block h / its half of block 0
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            PA[j] = umma::smem_u32(c.base) + (uint32_t)(S_ST + (quarter & 1) * ST_BYTES) + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128) +
+                    (uint32_t)(((j ^ row) & 7) << 4);
+            PH[j] = PA[j] + (uint32_t)h * QBLK;
+        }
+#pragma unroll
+        for (int c_ = 0; c_ < 4; ++c_) PQ[c_] = h ? PA[4 + c_] : PA[c_];
+        const uint64_t dA0 = umma::desc_mn(c.base + S_ST + (quarter & 1) * ST_BYTES + ST_A, 0, QBLK);
+        const uint64_t dB0 = umma::desc_mn(c.base + S_ST + (quarter & 1) * ST_BYTES + ST_B, 0, QBLK);
         constexpr uint32_t LO_STEP = (2 * QBLK) >> 4, KS_STEP = (16 * 128) >> 4;
-        auto stage_done = [&](int L, uint32_t lay) {
+        auto prod_begin = [&](uint32_t prod) {
+            c.ok &= umma::mbar_wait_spin(c.bars + B_FREE0 + ((quarter + 2) & 3), quarter >= 2 ? (prod & 1u) : ((prod + 1u) & 1u));
+        };
+        auto prod_end = [&](int PK, uint32_t prod, uint32_t lay) {
             umma::fence_proxy_async();
             asm volatile("bar.sync %0, 64;" ::"r"(3 + quarter) : "memory");
-            if (h == 0 && (tid & 31) == 0) {
+            if (h == 0 && lane == 0) {
                 umma::fence_after_sync();
-                if (quarter == 0) c.ok &= umma::mbar_wait_spin(c.bars + B_DWFREE, (lay + 1u) & 1u);   // DW of the previous layer read out
-                const uint32_t idesc_w = umma::idesc_bf16(128, L == 0 ? N_X3 : (L == 1 ? D_H : 64), 1, 1);
-                constexpr uint32_t idesc_u = umma::idesc_bf16(128, 16, 1, 1);
-                const uint32_t col_u = c.tmem + (uint32_t)(T_DW + (L == 0 ? N_X3 : 64));
-                const uint64_t db = L == 2 ? dh0 : dx0;                      // B of the wide product: X (layers 3, 2) or e = first block of HS
-                const uint32_t acc0 = quarter == 0 ? 0u : 1u;
+                if (quarter == 0) {
+                    if (PK == 0 || PK == 2 || PK == 3) c.ok &= umma::mbar_wait_spin(c.bars + B_DWFREE, (lay + 1u) & 1u);   // previous layer read out
+                } else {
+                    c.ok &= umma::mbar_wait_spin(c.bars + B_ISS0 + quarter - 1, prod & 1u);
+                }
+                const int n_out = PK == 0 ? N_X3 : (PK == 2 ? D_H : (PK == 3 ? 64 : 16));
+                const uint32_t idesc = umma::idesc_bf16(128, n_out, 1, 1);
+                const uint32_t dcol = c.tmem + (uint32_t)(T_DW + (PK == 1 ? N_X3 : (PK == 4 ? 64 : 0)));
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
                     const int pass = j >> 1, ks = j & 1;
-                    umma::mma_ss(c.tmem + T_DW, dz0 + (uint64_t)((pass == 1 ? LO_STEP : 0) + ks * KS_STEP),
-                                 db + (uint64_t)((pass == 2 ? LO_STEP : 0) + ks * KS_STEP), idesc_w, j == 0 ? acc0 : 1u);
+                    umma::mma_ss(dcol, dA0 + (uint64_t)((pass == 1 ? LO_STEP : 0) + ks * KS_STEP),
+                                 dB0 + (uint64_t)((pass == 2 ? LO_STEP : 0) + ks * KS_STEP), idesc, (j == 0 && quarter == 0) ? 0u : 1u);
                 }
-                if (L != 1) {
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        const int pass = j >> 1, ks = j & 1;
-                        umma::mma_ss(col_u, dh0 + (uint64_t)((pass == 1 ? LO_STEP : 0) + ks * KS_STEP),
-                                     du0 + (uint64_t)((pass == 2 ? LO_STEP : 0) + ks * KS_STEP), idesc_u, j == 0 ? acc0 : 1u);
-                    }
-                }
+                umma::mbar_arrive(c.bars + B_ISS0 + quarter);
                 umma::commit(c.bars + B_FREE0 + quarter);
-                if (quarter == 3) umma::commit(c.bars + B_DWRDY);
+                if (PK == 1 || PK == 2 || PK == 4) umma::commit(c.bars + B_DWRDY);       // (covers this thread's MMAs of P - 1 too)
             }
+        };
+        // U = [dlogits 5 | dRGB 3 | 0 x 8] -> features 0 .. 15 of the B tile; the h = 0 thread writes the hi part, h = 1 the lo part
+        auto put_u = [&](const uint32_t (&uh)[4], const uint32_t (&ul)[4]) {
+            if (h == 0) { sts128<ST_B>(PA[0], uh[0], uh[1], uh[2], uh[3]); sts128<ST_B>(PA[1], 0u, 0u, 0u, 0u); }
+            else { sts128<ST_B + 2 * (int)QBLK>(PA[0], ul[0], ul[1], ul[2], ul[3]); sts128<ST_B + 2 * (int)QBLK>(PA[1], 0u, 0u, 0u, 0u); }
+        };
+        // W1 image -> staging buffer 0 by the TMA (async proxy: no thread copies anything); issued by one thread
+        auto load_w1 = [&]() {
+            umma::fence_proxy_async();
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(c.bars + B_W1)), "r"(2 * IMG_BLOCK) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(umma::smem_u32(c.base + S_ST)), "l"(f.tc_img + IMG_W1_HI), "r"(2 * IMG_BLOCK), "r"(umma::smem_u32(c.bars + B_W1))
+                         : "memory");
         };
         uint32_t* scr_p = scratch + (size_t)blockIdx.x * SCR_CTA_WORDS + p;
         // copy this thread's 64 dZ features (two 32-feature groups) from an operand region into the Z staging tile
@@ -294,10 +323,6 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
             }
             umma::wait_ld();
         };
-        uint32_t P[8];                                 // chunk addresses of this thread's row in block h (see sts128)
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            P[j] = umma::smem_u32(c.base) + (uint32_t)h * QBLK + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128) + (uint32_t)(((j ^ row) & 7) << 4);
 
         int64_t i_next = 0;
         { const int64_t s0 = (int64_t)blockIdx.x * TC_TP + p; if (s0 < N) i_next = am(s0); }
@@ -308,7 +333,14 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
             { const int64_t s1 = slot + (int64_t)gridDim.x * TC_TP; i_next = s1 < N ? am(s1) : 0; }
             // (prefetching the next tile's cached operand words into L2 here shortened the load phase by 2 k cycles but cost more in
             // load / store unit traffic than it saved: 0.287 vs 0.273 ms)
-            const uint32_t lay0 = 3u * k;                                   // global layer counter of this tile's first wgrad
+            const uint32_t lay0 = 3u * k, prod0 = 5u * k;                   // global layer / product counters of this tile
+            if (ctid == 0) {                                                // W1 -> staging buffer 0 (last used by quarters 0 and 2 of product 4)
+                if (k > 0) {
+                    c.ok &= umma::mbar_wait_spin(c.bars + B_FREE0 + 0, (prod0 - 1u) & 1u);
+                    c.ok &= umma::mbar_wait_spin(c.bars + B_FREE0 + 2, (prod0 - 1u) & 1u);
+                }
+                load_w1();
+            }
             B2_MARK(0);
             float g[3], gs[7];                                 // d loss / d (rgb 3 | sdf, entropy, prob[5])
             {
@@ -367,7 +399,10 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
             float v[32];
             uint32_t mask1[2], mask3[2];
             // ---- forward layer 1 ----
-            round([&]() { issue_fwd(c, IMG_W1_HI, IMG_W1_LO, 4, [](int ks, bool lo) { return (lo ? T_R1_LO : T_R1_HI) + 8 * ks; }); });
+            round([&]() {
+                c.ok &= umma::mbar_wait_spin(c.bars + B_W1, k & 1u);           // the W1 image has landed in staging buffer 0
+                issue_fwd(c, W1H, W1L, 4, [](int ks, bool lo) { return (lo ? T_R1_LO : T_R1_HI) + 8 * ks; });
+            });
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
                 const int f0 = 64 * h + 32 * cc;
@@ -390,7 +425,7 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
             }
             B2_MARK(2);
             // ---- forward layer 2 ----
-            round([&]() { issue_fwd(c, IMG_W2_HI, IMG_W2_LO, 8, [](int ks, bool lo) { return (lo ? T_R1_LO : T_R1_HI) + 8 * ks; }); });
+            round([&]() { issue_fwd(c, W2H, W2L, 8, [](int ks, bool lo) { return (lo ? T_R1_LO : T_R1_HI) + 8 * ks; }); });
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
                 const int f0 = 64 * h + 32 * cc;
@@ -409,7 +444,7 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
             B2_MARK(3);
             // ---- forward layer 3 ----
             round([&]() {
-                issue_fwd(c, IMG_W3_HI, IMG_W3_LO, 6, [](int ks, bool lo) {
+                issue_fwd(c, W3H, W3L, 6, [](int ks, bool lo) {
                     return ks < 4 ? (lo ? T_R2_LO : T_R2_HI) + 8 * ks : (lo ? T_G_LO : T_G_HI) + 8 * (ks - 4);
                 });
             });
@@ -506,44 +541,39 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
             chain_sync();
             if (ctid == 0) {
                 umma::fence_after_sync();
-                issue_dgrad(c, T_R1_HI, T_R1_LO, IMG_W3_HI, IMG_W3_LO, D_SDF_IN);
+                issue_dgrad(c, T_R1_HI, T_R1_LO, W3H, W3L, D_SDF_IN);
                 umma::commit(c.bars + B_DG3);
             }
-            // ... meanwhile: hand-off of layer 3: Z = dZ3 (R1), X = [sdf_emb | grid | 1 | U] (R2), second A operand = H3 (parked).
-            // Everything is in registers before the wait; the critical section is shared-memory stores only.
+            // ... meanwhile, the two products of layer 3.  P0: A = dZ3 (R1), B = [sdf_emb | grid | 1] (R2); everything is in registers
+            // before the wait, the critical section is shared-memory stores only.
             {
-                uint32_t ah[2][16], al[2][16], zh[2][16], zl[2][16];
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) scr_load(scr_p, SCR_H3, 64, 32 * h + 16 * cc, ah[cc], al[cc]);
+                uint32_t zh[2][16], zl[2][16], xh[2][16], xl[2][16];
                 load_z(T_R1_HI, T_R1_LO, zh, zl);
-                if (prof && blockIdx.x == 0 && k == 1 && (tid & 31) == 0 && h == 0) prof[32 + 4 * quarter] = clock64();
-                stage_wait(lay0);
-                if (prof && blockIdx.x == 0 && k == 1 && (tid & 31) == 0 && h == 0) prof[33 + 4 * quarter] = clock64();
-                if (prof && blockIdx.x == 0 && k == 1 && (tid & 31) == 0 && h == 1) prof[60 + quarter] = clock64();
-                put64<S_ZS>(P, zh, zl);
-                put64<S_HS>(P, ah, al);
-                // x3 words of this thread (reuse zh / zl): h = 0 sdf_emb (64 features), h = 1 grid (32) + [1 | 0.. | U]
                 if (h == 0) {
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        umma::tmem_ld16(c.lane_base + T_R2_HI + 16 * cc, zh[cc]); umma::tmem_ld16(c.lane_base + T_R2_LO + 16 * cc, zl[cc]);
-                    }
-                    umma::wait_ld();
-                    put64<S_XS>(P, zh, zl);
+                    for (int cc = 0; cc < 2; ++cc) { umma::tmem_ld16(c.lane_base + T_R2_HI + 16 * cc, xh[cc]); umma::tmem_ld16(c.lane_base + T_R2_LO + 16 * cc, xl[cc]); }
                 } else {
-                    umma::tmem_ld16(c.lane_base + T_G_HI, zh[0]); umma::tmem_ld16(c.lane_base + T_G_LO, zl[0]);
+                    umma::tmem_ld16(c.lane_base + T_G_HI, xh[0]); umma::tmem_ld16(c.lane_base + T_G_LO, xl[0]);
 #pragma unroll
-                    for (int t = 0; t < 16; ++t) { zh[1][t] = 0u; zl[1][t] = 0u; }
-                    zh[1][0] = 0x00003F80u;                                  // feature 96 = 1.0 (bf16): bias column of sdf_linear.0
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) { zh[1][8 + t] = uh[t]; zl[1][8 + t] = ul[t]; }  // features 112 .. 119 = U
-                    umma::wait_ld();
-                    put64<S_XS>(P, zh, zl);
+                    for (int t = 0; t < 16; ++t) { xh[1][t] = 0u; xl[1][t] = 0u; }
+                    xh[1][0] = 0x00003F80u;                                  // feature 96 = 1.0 (bf16): bias column of sdf_linear.0
                 }
-                if (prof && blockIdx.x == 0 && k == 1 && (tid & 31) == 0 && h == 0) prof[34 + 4 * quarter] = clock64();
-                stage_done(0, lay0);
-                if (prof && blockIdx.x == 0 && k == 1 && (tid & 31) == 0 && h == 0) prof[35 + 4 * quarter] = clock64();
-                if (prof && blockIdx.x == 0 && k == 1 && (tid & 31) == 0 && h == 1) prof[56 + quarter] = clock64();
+                umma::wait_ld();
+                if (prof && blockIdx.x == 0 && k == 1 && lane == 0 && h == 0) prof[32 + 4 * quarter] = clock64();
+                prod_begin(prod0);
+                if (prof && blockIdx.x == 0 && k == 1 && lane == 0 && h == 0) prof[33 + 4 * quarter] = clock64();
+                put64<ST_A>(PH, zh, zl);
+                put64<ST_B>(PH, xh, xl);
+                if (prof && blockIdx.x == 0 && k == 1 && lane == 0 && h == 0) prof[34 + 4 * quarter] = clock64();
+                prod_end(0, prod0, lay0);
+                if (prof && blockIdx.x == 0 && k == 1 && lane == 0 && h == 0) prof[35 + 4 * quarter] = clock64();
+                // P1: A = H3 (parked), B = U
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) scr_load(scr_p, SCR_H3, 64, 32 * h + 16 * cc, zh[cc], zl[cc]);
+                prod_begin(prod0 + 1u);
+                put64<ST_A>(PH, zh, zl);
+                put_u(uh, ul);
+                prod_end(1, prod0 + 1u, lay0);
             }
             B2_MARK(6);
             c.ok &= umma::mbar_wait_spin(c.bars + B_DG3, k & 1u);
@@ -571,20 +601,20 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
             if (ctid == 0) {
                 c.ok &= umma::mbar_wait_spin(c.bars + B_DCONS, k & 1u);
                 umma::fence_after_sync();
-                issue_dgrad(c, T_R2_HI, T_R2_LO, IMG_W2_HI, IMG_W2_LO, D_H);
+                issue_dgrad(c, T_R2_HI, T_R2_LO, W2H, W2L, D_H);
                 umma::commit(c.bars + B_MMA);
             }
             B2_MARK(8);
-            // ... meanwhile: hand-off of layer 2: Z = dH (R2), X = H1 (parked)
+            // ... meanwhile, P2: A = dH (R2), B = H1 (parked)
             {
                 uint32_t ah[2][16], al[2][16], zh[2][16], zl[2][16];
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) scr_load(scr_p, SCR_H1, 64, 32 * h + 16 * cc, ah[cc], al[cc]);
                 load_z(T_R2_HI, T_R2_LO, zh, zl);
-                stage_wait(lay0 + 1u);
-                put64<S_ZS>(P, zh, zl);
-                put64<S_XS>(P, ah, al);
-                stage_done(1, lay0 + 1u);
+                prod_begin(prod0 + 2u);
+                put64<ST_A>(PH, zh, zl);
+                put64<ST_B>(PH, ah, al);
+                prod_end(2, prod0 + 2u, lay0 + 1u);
             }
             c.ok &= umma::mbar_wait_spin(c.bars + B_MMA, ph_mma);
             ph_mma ^= 1;
@@ -603,35 +633,41 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
                 st_op(c, T_R1_HI, T_R1_LO, f0, zh, zl);
             }
             umma::wait_st();
-            // ---- hand-off of layer 1: Z = dZ1 (R1), second A operand = [e (ones in slot 15) | rgb_emb], X = e = its first block, U ----
+            // ---- the two products of layer 1.  P3: A = dZ1 (R1), B = e (ones in slot 15: bias column);
+            //      P4: A = [e | rgb_emb (parked)] (the ones row gives both head biases), B = U.  Thread h owns slot groups 2h, 2h+1 of
+            //      e (its half of block 0) and half h of rgb_emb (block 1) ----
             {
-                uint32_t zh[2][16], zl[2][16];
+                uint32_t zh[2][16], zl[2][16], eh[2][8], el[2][8], rh[16], rl[16];
                 load_z(T_R1_HI, T_R1_LO, zh, zl);
-                if (h == 0) {
-                    uint32_t eh[4][8], el[4][8];
+                e_words(2 * h, eh[0], el[0]); e_words(2 * h + 1, eh[1], el[1]);
+                if (h == 0) { eh[0][7] = (eh[0][7] & 0x0000ffffu) | 0x3F800000u; el[0][7] &= 0x0000ffffu; }   // slot 15 = 1.0
+                scr_load(scr_p, SCR_RGB, 32, 16 * h, rh, rl);
+                prod_begin(prod0 + 3u);
+                put64<ST_A>(PH, zh, zl);
 #pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) e_words(qq, eh[qq], el[qq]);
-                    eh[0][7] = (eh[0][7] & 0x0000ffffu) | 0x3F800000u; el[0][7] &= 0x0000ffffu;  // slot 15 = 1.0: bias column / row
-                    stage_wait(lay0 + 2u);
-                    put64<S_ZS>(P, zh, zl);
-                    put16<S_HS, 0>(P, eh[0]); put16<S_HS, 1>(P, eh[1]); put16<S_HS, 2>(P, eh[2]); put16<S_HS, 3>(P, eh[3]);
-                    put16<S_HS + 2 * (int)QBLK, 0>(P, el[0]); put16<S_HS + 2 * (int)QBLK, 1>(P, el[1]);
-                    put16<S_HS + 2 * (int)QBLK, 2>(P, el[2]); put16<S_HS + 2 * (int)QBLK, 3>(P, el[3]);
-                } else {
-                    uint32_t ah[2][16], al[2][16];
+                for (int sg = 0; sg < 2; ++sg)
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) scr_load(scr_p, SCR_RGB, 32, 16 * cc, ah[cc], al[cc]);
-                    stage_wait(lay0 + 2u);
-                    put64<S_ZS>(P, zh, zl);
-                    put64<S_HS>(P, ah, al);
+                    for (int c_ = 0; c_ < 2; ++c_) {
+                        sts128<ST_B>(PQ[2 * sg + c_], eh[sg][4 * c_], eh[sg][4 * c_ + 1], eh[sg][4 * c_ + 2], eh[sg][4 * c_ + 3]);
+                        sts128<ST_B + 2 * (int)QBLK>(PQ[2 * sg + c_], el[sg][4 * c_], el[sg][4 * c_ + 1], el[sg][4 * c_ + 2], el[sg][4 * c_ + 3]);
+                    }
+                prod_end(3, prod0 + 3u, lay0 + 2u);
+                prod_begin(prod0 + 4u);
 #pragma unroll
-                    for (int t = 0; t < 16; ++t) { ah[0][t] = 0u; al[0][t] = 0u; }
+                for (int sg = 0; sg < 2; ++sg)
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) { ah[0][8 + t] = uh[t]; al[0][8 + t] = ul[t]; }
-                    put32<S_XS, 1>(P, ah[0]); put32<S_XS + 2 * (int)QBLK, 1>(P, al[0]);
+                    for (int c_ = 0; c_ < 2; ++c_) {
+                        sts128<ST_A>(PQ[2 * sg + c_], eh[sg][4 * c_], eh[sg][4 * c_ + 1], eh[sg][4 * c_ + 2], eh[sg][4 * c_ + 3]);
+                        sts128<ST_A + 2 * (int)QBLK>(PQ[2 * sg + c_], el[sg][4 * c_], el[sg][4 * c_ + 1], el[sg][4 * c_ + 2], el[sg][4 * c_ + 3]);
+                    }
+#pragma unroll
+                for (int c_ = 0; c_ < 4; ++c_) {
+                    sts128<ST_A + (int)QBLK>(PQ[c_], rh[4 * c_], rh[4 * c_ + 1], rh[4 * c_ + 2], rh[4 * c_ + 3]);
+                    sts128<ST_A + 3 * (int)QBLK>(PQ[c_], rl[4 * c_], rl[4 * c_ + 1], rl[4 * c_ + 2], rl[4 * c_ + 3]);
                 }
+                put_u(uh, ul);
+                prod_end(4, prod0 + 4u, lay0 + 2u);
             }
-            stage_done(2, lay0 + 2u);
             B2_MARK(10);
             umma::fence_before_sync();
             chain_sync();          // every accumulator / operand read of this tile is done before the next tile's stores

@@ -27,7 +27,7 @@ buf = (C.c_longlong * 64)()
 L.call("mf_debug_profile", 0, C.cast(buf, C.c_void_p))
 t = list(buf)
 names = ["load idx, d_raw, e/grid words", "L1 + epi1 (H1 -> R1, scratch)", "L2 + epi2", "L3 + epi3 (logits, H3 -> scratch)", "softmax + dZ3 -> R1",
-         "issue dgrad3 + hand-off 3", "dgrad3 wait", "dH -> R2 + issue dgrad2", "hand-off 2 + dgrad2 wait", "dZ1 -> R1 + hand-off 1"]
+         "issue dgrad3 + products 0, 1", "dgrad3 wait", "dH -> R2 + issue dgrad2", "product 2 + dgrad2 wait", "dZ1 -> R1 + products 3, 4"]
 for i in range(10):
     print(f"chain {names[i]:28s} {t[i+1]-t[i]:8d} cycles")
 print("chain tile total", t[10] - t[0])
@@ -35,7 +35,6 @@ for L_ in range(3):
     print(f"wgrad layer {3 - L_}: ready at +{t[16+L_]-t[0]:d}, read-out {t[20+L_]-t[16+L_]:d} cycles")
 print(f"scatter: dgrad3 seen at +{t[24]-t[0]:d}, released at +{t[26]-t[0]:d}, reductions take {t[25]-t[26]:d} cycles")
 
-print("hand-off 3, per quarter (h = 0 warp): [regs ready, buffer free, stores done, fence+arrive done] relative to tile start")
+print("product 0, per quarter (h = 0 warp): [regs ready, buffer free, stores done, MMAs issued] relative to tile start")
 for q in range(4):
     print("  q%d" % q, [t[32 + 4 * q + j] - t[0] for j in range(4)])
-print("h = 1 warp: [buffer free seen, arrived]", [[t[60 + q] - t[0], t[56 + q] - t[0]] for q in range(4)])
