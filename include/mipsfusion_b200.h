@@ -232,6 +232,10 @@ int mf_gen_rays_packed(const float* rays7, const float* poses, const int64_t* po
 /* d_poses (K,4,4) += backward of mf_gen_rays (rotation block and translation column). */
 int mf_gen_rays_bwd(const float* dirs_cam, const int64_t* pose_idx, const float* d_rays_o, const float* d_rays_d,
                     float* d_poses, int64_t R, int K, void* stream);
+/* The same for the packed batch of mf_gen_rays_packed: the camera directions are the first 3 of the 7 floats of a ray record
+ * (mipsfusion.py:289-290).  This is the pose-gradient leg of the mapping loop's backward (mipsfusion.py:275-282,338-342). */
+int mf_gen_rays_packed_bwd(const float* rays7, const int64_t* pose_idx, const float* d_rays_o, const float* d_rays_d,
+                           float* d_poses, int64_t R, int K, void* stream);
 
 /* ---- N1 (first "next" row of SURVEY 8): keyframe ray store on the device (model/keyframeSet.py:25,76-79,170-175,386-437) ----
  * mf_kf_store: add_keyframe -- store_slot (n_rays,7) = [dir_cam | rgb | depth] of the pixels (rows[j], cols[j]) of a

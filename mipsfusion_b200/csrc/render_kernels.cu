@@ -364,20 +364,45 @@ __global__ void gen_rays_kernel(const float* __restrict__ dirs, int ld, const fl
     }
 }
 
-__global__ void gen_rays_bwd_kernel(const float* __restrict__ dirs, const int64_t* __restrict__ pose_idx,
-                                    const float* __restrict__ d_o, const float* __restrict__ d_d,
-                                    float* __restrict__ d_poses, int64_t R, int K) {
+// d_poses (K,4,4) += backward of gen_rays: rotation block d_R[j][k] += d_d[r][j] * dir[r][k], translation d_t[j] += d_o[r][j].
+// Rays of one keyframe are summed in shared memory first (up to GRB_MAX_K poses per launch; beyond that straight to global):
+// one global atomic per (block, pose, entry) instead of twelve per ray.
+constexpr int GRB_MAX_K = 64;
+__global__ void __launch_bounds__(256) gen_rays_bwd_kernel(const float* __restrict__ dirs, int dir_stride, const int64_t* __restrict__ pose_idx,
+                                                           const float* __restrict__ d_o, const float* __restrict__ d_d,
+                                                           float* __restrict__ d_poses, int64_t R, int K) {
+    __shared__ float acc[GRB_MAX_K * 12];
+    const bool use_smem = K <= GRB_MAX_K;
+    if (use_smem) {
+        for (int i = threadIdx.x; i < K * 12; i += blockDim.x) acc[i] = 0.f;
+        __syncthreads();
+    }
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    int64_t pi = pose_idx ? pose_idx[r] : 0;
-    if (pi < 0) pi += K;
-    float* P = d_poses + pi * 16;
+    if (r < R) {
+        int64_t pi = pose_idx ? pose_idx[r] : 0;
+        if (pi < 0) pi += K;
+        const float dv[3] = {dirs[r * dir_stride], dirs[r * dir_stride + 1], dirs[r * dir_stride + 2]};
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const float g = d_d[r * 3 + j];
+        for (int j = 0; j < 3; ++j) {
+            const float g = d_d[r * 3 + j];
+            if (use_smem) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) atomicAdd(&P[j * 4 + k], g * dirs[r * 3 + k]);
-        atomicAdd(&P[j * 4 + 3], d_o[r * 3 + j]);
+                for (int k = 0; k < 3; ++k) atomicAdd(&acc[pi * 12 + j * 4 + k], g * dv[k]);
+                atomicAdd(&acc[pi * 12 + j * 4 + 3], d_o[r * 3 + j]);
+            } else {
+                float* P = d_poses + pi * 16;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) atomicAdd(&P[j * 4 + k], g * dv[k]);
+                atomicAdd(&P[j * 4 + 3], d_o[r * 3 + j]);
+            }
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < K * 12; i += blockDim.x) {
+            const float v = acc[i];
+            if (v != 0.f) atomicAdd(&d_poses[(i / 12) * 16 + (i % 12)], v);
+        }
     }
 }
 
@@ -465,7 +490,17 @@ MF_API int mf_gen_rays_bwd(const float* dirs_cam, const int64_t* pose_idx, const
     MF_CHECK_ARG(R >= 0 && K >= 1);
     if (R == 0) return MF_OK;
     MF_CHECK_ARG(dirs_cam && d_rays_o && d_rays_d && d_poses);
-    gen_rays_bwd_kernel<<<(unsigned)((R + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dirs_cam, pose_idx, d_rays_o, d_rays_d, d_poses, R, K);
+    gen_rays_bwd_kernel<<<(unsigned)((R + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dirs_cam, 3, pose_idx, d_rays_o, d_rays_d, d_poses, R, K);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}
+
+MF_API int mf_gen_rays_packed_bwd(const float* rays7, const int64_t* pose_idx, const float* d_rays_o, const float* d_rays_d,
+                                  float* d_poses, int64_t R, int K, void* stream) {
+    MF_CHECK_ARG(R >= 0 && K >= 1);
+    if (R == 0) return MF_OK;
+    MF_CHECK_ARG(rays7 && d_rays_o && d_rays_d && d_poses);
+    gen_rays_bwd_kernel<<<(unsigned)((R + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rays7, 7, pose_idx, d_rays_o, d_rays_d, d_poses, R, K);
     MF_LAUNCH_CHECK();
     return MF_OK;
 }

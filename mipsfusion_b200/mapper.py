@@ -56,6 +56,7 @@ class FusedMapper:
                 warnings.warn("FusedMapper: peer memory unavailable (%s); using NCCL all-reduce" % (e,))
                 self.arena = None
         self.step_count = 0
+        self.pose_grad_impl = "tc"       # "tc": tensor-core backward (pose gradients 2.4e-4 vs the oracle), "fp32": CUDA cores (5e-7)
         self._bufs = {}
         self.timing = None            # optional dict name -> (start_event, end_event) lists
         self.launches = 0
@@ -113,9 +114,12 @@ class FusedMapper:
         f = self.model._field(keep=(self.grid, self.prep))
         return f
 
-    def step(self, rays_o, rays_d, target_rgb, target_d, u=None, EMD_w=0.01, update=True):
+    def step(self, rays_o, rays_d, target_rgb, target_d, u=None, EMD_w=0.01, update=True, ray_grads=None):
         """One mapping iteration on device tensors (rays_o/rays_d (R,3), target_rgb (R,3), target_d (R,) or (R,1)).
-        Returns the (8,) device tensor [rgb_loss, depth_loss, sdf_loss, fs_loss, psnr, fs_w, sdf_w, n_valid]."""
+        Returns the (8,) device tensor [rgb_loss, depth_loss, sdf_loss, fs_loss, psnr, fs_w, sdf_w, n_valid].
+        ray_grads: optional pair of (R,3) device tensors that receive d loss / d rays_o and d loss / d rays_d (the pose-gradient
+        leg of the reference's BA loop, mipsfusion.py:275-282,338-342).  ``self.pose_grad_impl`` selects the backward that
+        produces them: "fp32" (CUDA-core decoder, 1e-6 against the oracle per ray) or "tc" (tensor cores)."""
         model = self.model
         R = rays_o.shape[0]
         cfg, lins = model._render_cfg(True, EMD_w, self.dev)
@@ -147,8 +151,15 @@ class FusedMapper:
         L.call("mf_render_loss_bwd", L.ptr(b["raw"]), L.ptr(b["z"]), L.ptr(target_rgb), L.ptr(target_d), L.ptr(b["counts"]),
                L.ptr(b["losses"]), C.byref(cfg), L.ptr(self.loss_w), None, None, L.ptr(b["d_raw"]), R, S, st)
         e3 = ev()
-        L.call("mf_field_query_rays_bwd", L.ptr(rays_o), L.ptr(rays_d), L.ptr(b["z"]), C.byref(field), L.ptr(b["d_raw"]),
-               L.ptr(b["feat"]), L.ptr(self.g_grid), L.ptr(self.g_mlp), None, None, L.ptr(_Workspace.get(self.dev, field_points=R * S)), R, S, st)
+        if ray_grads is None:
+            L.call("mf_field_query_rays_bwd", L.ptr(rays_o), L.ptr(rays_d), L.ptr(b["z"]), C.byref(field), L.ptr(b["d_raw"]),
+                   L.ptr(b["feat"]), L.ptr(self.g_grid), L.ptr(self.g_mlp), None, None, L.ptr(_Workspace.get(self.dev, field_points=R * S)), R, S, st)
+        else:
+            fb = field if self.pose_grad_impl == "tc" else self.model._field(keep=(self.grid, self.prep), impl=1)
+            L.call("mf_field_query_rays_bwd", L.ptr(rays_o), L.ptr(rays_d), L.ptr(b["z"]), C.byref(fb), L.ptr(b["d_raw"]),
+                   L.ptr(b["feat"]) if self.pose_grad_impl == "tc" else None, L.ptr(self.g_grid), L.ptr(self.g_mlp), L.ptr(ray_grads[0]), L.ptr(ray_grads[1]),
+                   L.ptr(_Workspace.get(self.dev, field_points=R * S, want_ray_grads=True)), R, S, st)
+            self.launches += 2            # zero-fill of the per-point gradients, reduction over the samples of a ray
         e4 = ev()
         self.launches += 9            # sample_z, field fwd, render+loss fwd (2), render+loss bwd, compaction (2), field bwd, partial reduce
         if update:
@@ -164,12 +175,16 @@ class FusedMapper:
                 tm.setdefault(name, []).append((a, c))
         return b["losses"]
 
-    def step_host(self, rays7, pose_idx, poses, EMD_w=0.01):
+    def step_host(self, rays7, pose_idx, poses, EMD_w=0.01, pose_grad=False):
         """One mapping iteration from the HOST batch of the reference's BA loop (mipsfusion.py:289-322):
         ``rays7`` (R,7) float32 host tensor [dir_cam | rgb | depth] (pinned memory makes the copy asynchronous),
         ``pose_idx`` (R,) int64 host tensor (keyframe slot of each ray, -1 = current frame = last pose) or None,
         ``poses`` (K,4,4) camera-to-submap poses on the device.  Copies the batch to the device, generates the rays,
-        runs :meth:`step` and returns the 8 loss terms as a host tensor (one synchronisation)."""
+        runs :meth:`step` and returns the 8 loss terms as a host tensor (one synchronisation).
+        pose_grad=True additionally returns d loss / d poses as a (K,4,4) device tensor (rows 0-2 filled: rotation block and
+        translation column; the ray gradients are pushed through the ray generation by mf_gen_rays_packed_bwd).  The
+        reference's loop feeds it to its pose parameters with ``poses_all.backward(d_poses)`` before ``pose_optimizer.step()``
+        (mipsfusion.py:327,338-342)."""
         R = rays7.shape[0]
         hb = self._bufs.get(("host", R))
         if hb is None:
@@ -185,10 +200,24 @@ class FusedMapper:
         L.call("mf_gen_rays_packed", L.ptr(hb["rays7"]), L.ptr(poses), L.ptr(hb["idx"]) if pose_idx is not None else None,
                L.ptr(hb["o"]), L.ptr(hb["d"]), L.ptr(hb["rgb"]), L.ptr(hb["depth"]), R, poses.shape[0], L.stream())
         self.launches += 1
-        losses = self.step(hb["o"], hb["d"], hb["rgb"], hb["depth"], EMD_w=EMD_w)
+        if not pose_grad:
+            losses = self.step(hb["o"], hb["d"], hb["rgb"], hb["depth"], EMD_w=EMD_w)
+            hb["out"].copy_(losses, non_blocking=True)
+            torch.cuda.current_stream(self.dev).synchronize()
+            return hb["out"]
+        if "d_o" not in hb:
+            hb["d_o"], hb["d_d"] = torch.empty_like(hb["o"]), torch.empty_like(hb["d"])
+        losses = self.step(hb["o"], hb["d"], hb["rgb"], hb["depth"], EMD_w=EMD_w, ray_grads=(hb["d_o"], hb["d_d"]))
+        d_poses = torch.zeros(poses.shape[0], 4, 4, device=self.dev, dtype=torch.float32)
+        L.call("mf_gen_rays_packed_bwd", L.ptr(hb["rays7"]), L.ptr(hb["idx"]) if pose_idx is not None else None, L.ptr(hb["d_o"]),
+               L.ptr(hb["d_d"]), L.ptr(d_poses), R, poses.shape[0], L.stream())
+        self.launches += 2
+        if self.world > 1:                                           # every rank holds the same poses: sum the gradients
+            D.allreduce_sum_(d_poses, self.group)
+            d_poses.mul_(1.0 / self.world)
         hb["out"].copy_(losses, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
-        return hb["out"]
+        return hb["out"], d_poses
 
     def step_from_store(self, store, first_kf_Id, related_kf_ids, poses_all, pix_num, cur_rays7=None, EMD_w=0.01, **draws):
         """One mapping iteration fed from the device-resident keyframe ray store (steps 3.1-3.4 of the reference's BA

@@ -142,3 +142,53 @@ def _dp_mapping(rank, ws):
 def test_data_parallel_mapping_recipe_matches_global_batch():
     errs = _run(_dp_mapping)
     assert max(errs.values()) < 1e-4, errs
+
+
+def _overlap_and_handoff(rank, ws):
+    """Submap-parallel placement (mipsfusion_b200.submap_parallel): the cross-rank overlap SDF difference equals the
+    single-process composition (loss and the gradient w.r.t. each submap's first-keyframe pose, which only its owner holds),
+    and a weight hand-off reproduces the source submap bit for bit.  The oracle fields play the models."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    import helpers as H
+    from oracle import overlap as oov
+    from mipsfusion_b200.submap_parallel import SubmapParallel
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "overlap.npz"))
+    cfg = H.make_config(int(fx["hash_size"]))
+    state = lambda i: {k[len(f"w{i}:"):]: torch.from_numpy(v) for k, v in fx.items() if k.startswith(f"w{i}:")}
+    models = [H.oracle_field(cfg, state(i)) for i in range(2)]
+    t = lambda k: torch.from_numpy(fx[k])
+    trunc = float(fx["trunc"])
+    sp = SubmapParallel(dist.group.WORLD)
+    assert [sp.owner(m) for m in range(4)] == [0, 1, 0, 1] and sp.local_ids(5) == [m for m in range(5) if m % ws == rank]
+    rays = t("rays")
+    target_d, dirs = rays[:, 6:7], rays[:, :3]
+    mask = torch.where(target_d > 0., torch.ones_like(target_d), torch.zeros_like(target_d))
+    f1 = t("first1").requires_grad_(True); f2 = t("first2").requires_grad_(True)
+    local = {m: models[m] for m in sp.local_ids(2)}                  # rank r owns submap r
+    loss = sp.overlap_sdf_difference(local, 0, 1, target_d, dirs, mask, t("ovlp"), f1, f2, trunc)
+    loss.backward()
+    mine = f1.grad if rank == 0 else f2.grad
+    other = f2.grad if rank == 0 else f1.grad
+    ok = abs(float(loss) - float(fx["loss"])) <= 2e-5 * abs(float(fx["loss"]))
+    ref = fx["g_first1"] if rank == 0 else fx["g_first2"]
+    ok &= float(np.abs(mine.numpy() - ref).max()) <= 2e-5 * float(np.abs(ref).max())
+    ok &= other is None                                              # the other submap's pose is a constant on this rank
+    # hand-off of submap 0 (rank 0) to rank 1: a module-like shim over the oracle field
+    class Shim:
+        pass
+    def shim(field):
+        s = Shim(); s.embed_fn = Shim(); s.decoder = Shim()
+        s.embed_fn.params = field.grid
+        s.decoder.ordered_params = lambda: [field.w[k] for k in field.w]
+        return s
+    dst_field = H.oracle_field(cfg, seed=99)
+    moved = sp.handoff(shim(models[0] if rank == 0 else dst_field), src=0, dst=1)
+    if rank == 1:
+        ok &= bool(torch.equal(dst_field.grid, models[0].grid)) and all(torch.equal(dst_field.w[k], models[0].w[k]) for k in dst_field.w)
+    ok &= moved == 4 * (models[0].grid.numel() + sum(v.numel() for v in models[0].w.values()))
+    return bool(ok)
+
+
+def test_submap_parallel_overlap_query_and_handoff():
+    assert all(_run(_overlap_and_handoff).values())
