@@ -293,11 +293,14 @@ def run_gpu(args):
     if world > 1:                      # the two other sharded paths, strong scaling on the single-GPU shapes
         also.update(tracking_bench(model, cfg, dev, group=group))
         also.update(joint_query_bench(dev, group=group))
+        also.update(joint_query_bench(dev, group=group, shard="submaps", prefix="joint_query_submap_sharded"))
+        also.update(submap_parallel_bench(dev, group))
     if world == 1:
         also.update(tracking_bench(model, cfg, dev))
         also.update(frame_bench(dev))
         also.update(joint_query_bench(dev))
         also.update(store_bench(mapper, dev, args.steps))
+        also.update(render_full_bench(dev))
     also_roof = {k[len("_roof_"):]: also.pop(k) for k in [k for k in also if k.startswith("_roof_")]}
     also_roof = {k: v for k, v in also_roof.items() if v}
 
@@ -342,7 +345,7 @@ def run_gpu(args):
                                      "note": "phase = Adam (grid + decoder, one launch) + weight re-layout",
                                      "traffic": traffic.get("adam_pair_kernel")}},
             "phase_ms": phase_ms}
-    for k in ("ro_field_query", "joint_query"):
+    for k in ("ro_field_query", "joint_query", "render_full_img"):
         if k in also_roof:
             also_roof[k]["frac"] = also_roof[k]["achieved"] / hbm
             roof["kernels"][k] = also_roof[k]
@@ -528,6 +531,121 @@ def cpu_also_baselines(cfg, also):
     return out
 
 
+def render_full_bench(dev):
+    """Logger.render_full_img (Logger.py:193-214) -- 620 x 460 rays x 75 samples in one forward launch; the
+    large-batch benchmark of the forward field kernel (21.4 M points)."""
+    import torch
+    import helpers as H
+    import mipsfusion_b200 as mf
+    from mipsfusion_b200 import synth
+    cfg = H.make_config(HASH, n_samples_d=50, n_range_d=25)
+    cfg["training"]["perturb"] = 0
+    model = H.cuda_model(cfg, H.state_of(H.oracle_field(cfg)), train=False)
+    dirs = synth.camera_rays()
+    c2w = synth.trajectory(4)[1]
+    frame = synth.render_frame(c2w, dirs)
+    dirs_d, depth_d, pose_d = dirs.to(dev), frame["depth"].to(dev), c2w.to(dev)
+    mf.render_full_img(model, dirs_d, pose_d, depth_d)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(3):
+        rgb, depth = mf.render_full_img(model, dirs_d, pose_d, depth_d)
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 3
+    R, Sx = dirs.shape[0] * dirs.shape[1], 75
+    return {"render_full_img_ms": ms, "render_full_img_rays_per_s": R / (ms * 1e-3),
+            "_roof_render_full_img": {"alg_bytes": ALG_BYTES_PER_POINT * R * Sx, "ms": ms, "achieved": ALG_BYTES_PER_POINT * R * Sx / (ms * 1e-3) / 1e9,
+                                      "what": f"{dirs.shape[1]} x {dirs.shape[0]} image, {R} rays x {Sx} samples: ray generation + z sampling + one forward "
+                                              "field launch over 21.4 M points + SDF-to-weight render (no losses); 1,024 B per point"},
+            "render_full_img_shape": f"{dirs.shape[1]}x{dirs.shape[0]} image (640x480 cropped by 10), {Sx} samples per ray, one launch"}
+
+
+def submap_parallel_bench(dev, group):
+    """BASELINE configs[3] (C4) pieces on G GPUs: 16 submaps placed round robin (2 per GPU at G = 8).
+    (a) weight hand-off of one T=2^19 submap (36.2 MB) rank 0 -> rank 1 and as a broadcast (mipsfusion.py:607-653);
+    (b) cross-rank overlap SDF difference with pose gradients, 768 rays (InactiveMap.py:128-192);
+    (c) rank 0 tracks + maps the active submap (the frame of frame_bench) while every other rank runs the inactive-submap BA
+        (InactiveMap.local_BA: 2600 rays x 75 samples per iteration) on its own submaps: rank-0 ms/frame and the BA iterations/s
+        of the other ranks, running concurrently."""
+    import torch
+    import torch.distributed as dist
+    import helpers as H
+    from mipsfusion_b200.mapper import FusedMapper
+    from mipsfusion_b200.submap_parallel import SubmapParallel
+    sp = SubmapParallel(group)
+    out = {}
+    cfg = H.make_config(HASH, n_samples_d=50, n_range_d=25)
+    of = H.oracle_field(cfg)
+    local_ids = sp.local_ids(16)
+    models = {m: H.cuda_model(cfg, H.state_of(of)) for m in local_ids[:2]}
+    m0 = models[local_ids[0]]
+    # (a) hand-off
+    for dst, key in ((1, "submap_handoff_p2p"), (None, "submap_handoff_broadcast")):
+        sp.handoff(m0, 0, dst)                                         # warm-up (NCCL channel set-up)
+        torch.cuda.synchronize(); dist.barrier(group=group)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            nbytes = sp.handoff(m0, 0, dst)
+        b.record(); torch.cuda.synchronize()
+        ms = _max_over_ranks(a.elapsed_time(b) / 5, dev, group)
+        out[key + "_ms"] = ms
+        out[key + "_gbs"] = 36.2e6 * 1.004 / (ms * 1e-3) / 1e9
+    # (b) cross-rank overlap query: submaps 0 and 1 (ranks 0 and 1), 768 rays
+    g = torch.Generator().manual_seed(5)
+    rays7 = H.synth_batch_packed(768, seed=3)[0].to(dev)
+    pose = H.synth_batch_packed(4, seed=3)[2][0].to(dev)
+    local = {m: models[m] for m in local_ids[:2] if m in (0, 1)}
+    for mm in local.values():
+        mm.eval()
+    target_d, dirs = rays7[:, 6:7].contiguous(), rays7[:, :3].contiguous()
+    mask = (target_d > 0).float()
+    def ovl():
+        f1 = torch.eye(4, device=dev).requires_grad_(True); f2 = torch.eye(4, device=dev).requires_grad_(True)
+        loss = sp.overlap_sdf_difference(local, 0, 1, target_d, dirs, mask, pose, f1, f2, 0.1)
+        if loss.requires_grad:
+            loss.backward()
+        return loss
+    for _ in range(3):
+        ovl()
+    torch.cuda.synchronize(); dist.barrier(group=group)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        ovl()
+    torch.cuda.synchronize()
+    out["overlap_query_ms"] = _max_over_ranks((time.perf_counter() - t0) / 10 * 1e3, dev, group)
+    out["overlap_query_shape"] = "768 rays, submaps 0 / 1 on ranks 0 / 1: two field queries + one 2 x 768-float all-reduce + pose gradients on each owner"
+    for mm in local.values():
+        mm.train()
+    # (c) rank 0: frames; other ranks: inactive-submap BA, concurrently
+    rank = sp.rank
+    frames = 6
+    torch.cuda.synchronize(); dist.barrier(group=group)
+    if rank == 0:
+        r = frame_bench(dev, frames=frames)
+        ms_frame, ba_its = r["ms_per_frame_640x480"], 0.0
+    else:
+        mapper = FusedMapper(m0)
+        ro, rd, rgb, d, _ = [t.to(dev).contiguous() for t in H.synth_batch(2600, 75, seed=10 + rank)]
+        for _ in range(3):
+            mapper.step(ro, rd, rgb, d.reshape(-1))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); n = 0
+        while time.perf_counter() - t0 < 0.25:                         # (about the span of rank 0's frames)
+            for _ in range(10):
+                mapper.step(ro, rd, rgb, d.reshape(-1))
+            torch.cuda.synchronize(); n += 10
+        ms_frame, ba_its = 0.0, n / (time.perf_counter() - t0)
+    tt = torch.tensor([ms_frame, ba_its], device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, group=group)
+    out["c4_ms_per_frame_rank0"] = float(tt[0])
+    out["c4_inactive_ba_iterations_per_s_other_ranks"] = float(tt[1])
+    out["c4_shape"] = ("16 submaps round robin; rank 0: RO 5 x 2000 x 384 + 10 pose-refinement iterations + mapping every 3rd frame on the "
+                       "active submap; ranks 1..G-1: InactiveMap.local_BA iterations (2600 rays x 75) on their submaps at the same time")
+    return out
+
+
 def emit(obj):
     """Write the single JSON line to the real stdout (fd 1 is pointed at stderr while the bench runs so that
     library banners such as NCCL's version line cannot pollute it)."""
@@ -565,7 +683,7 @@ def store_bench(mapper, dev, steps):
                                "mf_gen_rays_packed -> map step; no host data per step"}
 
 
-def joint_query_bench(dev, res=512, n_submaps=16, group=None):
+def joint_query_bench(dev, res=512, n_submaps=16, group=None, shard="points", prefix="joint_query"):
     """BASELINE configs[4] shape: joint SDF grid query at res^3 over n_submaps submaps (Mesher / render_mesh path):
     containment + world->submap transform + field query (sdf, entropy) + entropy/distance-weighted blend."""
     import numpy as np
@@ -588,7 +706,7 @@ def joint_query_bench(dev, res=512, n_submaps=16, group=None):
         poses.append(T); amin.append(a); amax.append(b); cents.append(((a + b) / 2).astype(np.float32))
     axes = [np.linspace(lo[k], hi[k], res) for k in range(3)]
     jq = mf.JointSubmapQuery(models, poses, amin, amax, cents)
-    kw = {} if group is None else dict(group=group, shard="points")
+    kw = {} if group is None else dict(group=group, shard=shard)
     jq.query(axes=[a_[:64] for a_ in axes], **kw)                # warm-up
     torch.cuda.synchronize()
     if group is not None:
@@ -609,6 +727,10 @@ def joint_query_bench(dev, res=512, n_submaps=16, group=None):
         roof = {"alg_bytes": jb, "ms": dt * 1e3, "achieved": jb / dt / 1e9, "evals": evals,
                 "what": f"{res}^3 grid x {n_submaps} submaps: containment + SDF-only field query of every (point, containing submap) "
                         "pair + blend; per pair 1,032 B" + ("" if group is None else " (all ranks)")}
+    if prefix != "joint_query":
+        return {prefix + "_grid_points_per_s": res ** 3 / dt, prefix + "_s": dt,
+                prefix + "_shape": f"{res}^3 grid x {n_submaps} submaps, submap m evaluated on GPU m mod G, partial sums (2 floats per grid "
+                                   "point) all-reduced (what the online system needs: the submaps live on different GPUs)"}
     return {"_roof_joint_query": roof, "joint_query_grid_points_per_s": res ** 3 / dt, "joint_query_s": dt,
             "joint_query_shape": f"{res}^3 grid x {n_submaps} submaps (T=2^{HASH} each), {frac:.2f} of the points inside >= 1 submap"
                                  + ("" if group is None else "; the grid points are sharded across the GPUs (strong scaling, results stay sharded)")}

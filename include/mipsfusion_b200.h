@@ -163,6 +163,8 @@ int64_t mf_feat_cache_size(int64_t n_points);
 int mf_field_query_rays(const float* rays_o, const float* rays_d, const float* z, const mf_field* field_host,
                         float* raw, void* feat, int64_t R, int S, void* stream);
 /* d_raw (R,S,10) -> grad_grid, grad_mlp (accumulate), d_rays_o / d_rays_d (R,3; optional, overwritten).
+ * grad_grid == grad_mlp == NULL with d_rays_o / d_rays_d given: ray gradients only (the gradient pose refinement of tracking,
+ * mipsfusion.py:501-556, needs nothing else; tensor-core decoder).
  * workspace: mf_field_bwd_workspace_size(R*S, d_rays_o != NULL) floats. */
 int mf_field_query_rays_bwd(const float* rays_o, const float* rays_d, const float* z, const mf_field* field_host,
                             const float* d_raw, const void* feat, float* grad_grid, float* grad_mlp, float* d_rays_o,
@@ -258,6 +260,18 @@ int mf_sample_distinct(int64_t n, int64_t k, uint32_t seed, int64_t* out, void* 
 int mf_kf_sample_rays(const float* store, int64_t n_rays, int64_t first_kf_id, const int64_t* other_kf_ids, int64_t n_other_kf,
                       int64_t last_kf_id, int n_related, int64_t n_first, int64_t n_other, int64_t n_last, uint32_t seed,
                       float* out_rays7, int64_t* out_kf_ids, int64_t* out_kf_indices, int64_t* out_idx, void* stream);
+
+/* ---- gradient pose refinement of tracking (mipsfusion.py:501-556; get_pose_param_optim :235-241, qt_to_transform_matrix
+ * geometry_helper.py:11-17) on the device.  state (32 floats): [0:4] quaternion (w,x,y,z), [4:7] translation, [7:14] Adam m,
+ * [14:21] Adam v, [21] step count, [22] best loss (< 0: none yet), [23] iterations since the best (thresh), [24] stopped flag,
+ * [25:32] spare.  best_c2w (16 floats) follows the reference: the pose whose loss was the smallest so far.
+ * mf_pose_to_c2w: state -> c2w (4,4), pytorch3d quaternion_to_matrix (no unit-norm assumption). */
+int mf_pose_to_c2w(const float* state, float* c2w, void* stream);
+/* One refinement update: losses (>= 4 floats: rgb, depth, sdf, fs) and loss_w (4) give the scalar the reference compares;
+ * best / thresh / stopped are updated exactly as the loop body does (:540-552); unless stopped, d_c2w (4,4) is pulled back to the
+ * quaternion and the translation and one torch.optim.Adam step (betas 0.9 / 0.999, eps 1e-8) with lr_rot / lr_trans is applied. */
+int mf_pose_refine_update(float* state, const float* c2w, const float* d_c2w, const float* losses, const float* loss_w,
+                          double lr_rot, double lr_trans, int wait_iters, float* best_c2w, void* stream);
 
 /* ---- a13: RandomOptimizer particle scoring (RandomOptimizer.py:54-73,81-85,113-131) ----
  * particles6 (C_total,6) pre-sampled template; search_size (6), rot_cur (3,3), trans_cur (3) device;

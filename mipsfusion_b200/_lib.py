@@ -97,6 +97,8 @@ PROTOTYPES = {
     "mf_gen_rays_packed": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
     "mf_gen_rays_bwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _P]),
     "mf_gen_rays_packed_bwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _P]),
+    "mf_pose_to_c2w": (_I, [_P, _P, _P]),
+    "mf_pose_refine_update": (_I, [_P, _P, _P, _P, _P, _D, _D, _I, _P, _P]),
     "mf_ro_score": (_I, [_P, _P, _P, _P, _P, _P, C.POINTER(Field), _D, _D, _I, _I, _I, _P, _P, _P, _P, _P]),
     "mf_ro_update": (_I, [_P, _P, _P, _I, _D, _P, _P, _P, _P, _P, _P]),
     "mf_joint_query_scratch_size": (_L, [_L]),

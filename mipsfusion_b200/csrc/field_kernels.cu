@@ -557,11 +557,23 @@ static int launch_field_bwd(const FieldDev& d, const Src& src, const float* d_ra
     ActiveMap am{nullptr, nullptr};
     int rc0 = compact_active_points(d_raw, N, scratch, &am, st); if (rc0) return rc0;
     if (d_pts) MF_CUDA(cudaMemsetAsync(d_pts, 0, (size_t)N * 3 * sizeof(float), st));   // skipped points: exactly zero
+    const bool params = grad_grid != nullptr;          // false: input gradients only (pose refinement)
+    if (!params && (d.impl == 1 || !d_pts)) {
+        mf_set_error("backward without parameter gradients needs the tensor-core decoder and a ray / point gradient output");
+        return MF_ERR_INVALID;
+    }
     if (d.impl != 1) {                                 // tcgen05 path: 128-point tiles, one CTA per SM
         const int64_t tiles = (N + TC_TP - 1) / TC_TP;
         const int64_t cap = mf_sm_count_cached();
         const int grid = (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
         mf_ktimer_begin(1, st);
+        if (!params) {
+            int rc = set_smem(field_bwd_tc_kernel<Src, true, false>, SMEM_TC_BWD); if (rc) return rc;
+            field_bwd_tc_kernel<Src, true, false><<<grid, TC_NT, SMEM_TC_BWD, st>>>(d, src, d_raw, nullptr, nullptr, d_pts, N, am, mf_tc_error_flag(), mf_tc_profile_buffer());
+            mf_ktimer_end(1, st);
+            MF_LAUNCH_CHECK();
+            return MF_OK;
+        }
         if (!d_pts && mf_bwd_impl() == 0) {                // role-split kernel (parameter gradients only)
             int rc = set_smem(field_bwd_tc2_kernel<Src>, b2::SMEM); if (rc) return rc;
             uint32_t* cta_scr = reinterpret_cast<uint32_t*>(scratch + act_scratch_words(N));
@@ -640,7 +652,8 @@ MF_API int mf_field_query_rays_bwd(const float* rays_o, const float* rays_d, con
                                    float* d_rays_d, float* workspace, int64_t R, int S, void* stream) {
     MF_CHECK_ARG(R >= 0 && S > 0);
     if (R == 0) return MF_OK;
-    MF_CHECK_ARG(rays_o && rays_d && z && d_raw && grad_grid && grad_mlp && workspace);
+    MF_CHECK_ARG(rays_o && rays_d && z && d_raw && workspace);
+    MF_CHECK_ARG((grad_grid == nullptr) == (grad_mlp == nullptr));      // both NULL: ray gradients only (needs d_rays_o / d_rays_d)
     MF_CHECK_ARG(((uintptr_t)grad_grid & 15) == 0);          // the scatter uses 16-byte reductions
     MF_CHECK_ARG((d_rays_o == nullptr) == (d_rays_d == nullptr));
     FieldDev d; int rc = mf_field_to_dev(field, &d); if (rc) return rc;

@@ -234,7 +234,9 @@ __device__ __forceinline__ void tb_wgrad_layer(TbCtx& c, int p, int q, const flo
 // ---------------------------------------------------------------------------------------------
 // The kernel.  part: [gridDim.x][MF_MLP_PARAMS] per-CTA partial parameter gradients (zeroed here).
 // ---------------------------------------------------------------------------------------------
-template <class Src, bool WANT_DX>
+// PARAMS = false (with WANT_DX): input gradients only -- the gradient pose refinement of tracking (mipsfusion.py:501-556) needs
+// d loss / d rays and nothing else: no wgrad products, no narrow-head reductions, no table scatter, W1 stays resident.
+template <class Src, bool WANT_DX, bool PARAMS = true>
 __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src src, const float* __restrict__ d_raw,
                                                                 float* __restrict__ grad_grid, float* __restrict__ part,
                                                                 float* __restrict__ d_pts, int64_t N_all, ActiveMap am,
@@ -242,10 +244,12 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x, p = tid & (TC_TP - 1), q = tid >> 7, lane = tid & 31;
 #define TB_MARK(k) do { if (prof && tid == 0 && blockIdx.x == 0 && tile == (int64_t)gridDim.x) prof[k] = clock64(); } while (0)
-    float* gpart = part + (size_t)blockIdx.x * MF_MLP_PARAMS;
-    for (int i = tid; i < MF_MLP_PARAMS; i += TC_NT) gpart[i] = 0.f;
+    float* gpart = PARAMS ? part + (size_t)blockIdx.x * MF_MLP_PARAMS : nullptr;
+    if (PARAMS)
+        for (int i = tid; i < MF_MLP_PARAMS; i += TC_NT) gpart[i] = 0.f;
     TbCtx c;
     tb_setup(c, smem_raw, f.tc_img);
+    if (!PARAMS) { tb_copy(c.r1, f.tc_img + IMG_W1_HI, 2 * IMG_BLOCK); umma::fence_proxy_async(); }   // (published by the first round's barrier)
     const float2* grid2 = reinterpret_cast<const float2*>(f.grid);
 
     const int64_t N = am.n(N_all);                     // active points only (ascending point indices in am.idx)
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
         const int64_t i = valid ? am(slot) : 0;
         TB_MARK(0);
         // ---- W1 image into region 1 (it doubles as the wgrad dZ tile later in the tile) ----
-        tb_copy(c.r1, f.tc_img + IMG_W1_HI, 2 * IMG_BLOCK);
+        if (PARAMS) tb_copy(c.r1, f.tc_img + IMG_W1_HI, 2 * IMG_BLOCK);
         // ---- upstream gradient of the colour outputs of this point (the sdf-head part is loaded at the heads) ----
         float g[3];
 #pragma unroll
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
             umma::tmem_st8(c.lane_base + TB_OP1_LO + 8 * q, lo);
             // colour head, e part: dWr[c][64 + e_index(slot)] += dRGB[c] e[slot]
 #pragma unroll 1
-            for (int ch = 0; ch < 3; ++ch) {
+            for (int ch = 0; ch < (PARAMS ? 3 : 0); ++ch) {
                 float t[16];
 #pragma unroll
                 for (int s = 0; s < 16; ++s) t[s] = g[ch] * e[s];
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
             tb_store_op32(c, TB_OP2_HI, TB_OP2_LO, q, v);                    // sdf_emb
         } else {                                                             // colour head, rgb_emb part
 #pragma unroll 1
-            for (int ch = 0; ch < 3; ++ch) {
+            for (int ch = 0; ch < (PARAMS ? 3 : 0); ++ch) {
                 float t[32];
 #pragma unroll
                 for (int k = 0; k < 32; ++k) t[k] = g[ch] * v[k];
@@ -416,14 +420,14 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
         }
         // sdf_linear.2 weight gradient: dW4[c][32q + l] += sum_p dz4[c] h3[l]; biases from the q == 0 warps
 #pragma unroll 1
-        for (int ch = 0; ch < N_CLASS; ++ch) {
+        for (int ch = 0; ch < (PARAMS ? N_CLASS : 0); ++ch) {
             float t[32];
 #pragma unroll
             for (int k = 0; k < 32; ++k) t[k] = dz4[ch] * v[k];
             atomicAdd(&gpart[OFF_WS2 + ch * D_H + 32 * q + lane], rs32(t, lane));
             if (q == 0) { const float b = warp_sum(dz4[ch]); if (lane == 0) atomicAdd(&gpart[OFF_BS2 + ch], b); }
         }
-        if (q == 0) {
+        if (PARAMS && q == 0) {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) { const float b = warp_sum(g[ch]); if (lane == 0) atomicAdd(&gpart[OFF_BR + ch], b); }
         }
@@ -445,13 +449,13 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
 #pragma unroll
             for (int k = 0; k < 32; ++k) v[k] = ((mask3 >> k) & 1u) ? v[k] : 0.f;
         }
-        { float t[32];
+        if (PARAMS) { float t[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) t[k] = v[k];
           atomicAdd(&gpart[OFF_BS1 + 32 * q + lane], rs32(t, lane)); }
         TB_MARK(5);
         // ---- layer 3: wgrad (X = [sdf_emb (operand 2), grid features]), then dgrad ----
-        tb_wgrad_layer(c, p, q, v,
+        if (PARAMS) tb_wgrad_layer(c, p, q, v,
             [&](uint32_t (&xh)[16], uint32_t (&xl)[16]) {
                 if (q < 2) { umma::tmem_ld16(c.lane_base + TB_OP2_HI + 16 * q, xh); umma::tmem_ld16(c.lane_base + TB_OP2_LO + 16 * q, xl); }
                 else if (q == 2) { umma::tmem_ld16(c.lane_base + TB_G_HI, xh); umma::tmem_ld16(c.lane_base + TB_G_LO, xl); }
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
                                     : ll == 1 ? make_float2(__uint_as_float(r[2]), __uint_as_float(r[3]))
                                     : ll == 2 ? make_float2(__uint_as_float(r[4]), __uint_as_float(r[5]))
                                               : make_float2(__uint_as_float(r[6]), __uint_as_float(r[7]));
-                    grid_level_bwd<WANT_DX>(x, dy, grid2, grad_grid, level_info(f, q * 4 + ll), dx);
+                    grid_level_bwd<WANT_DX, PARAMS>(x, dy, grid2, grad_grid, level_info(f, q * 4 + ll), dx);
                 }
             }
         }
@@ -488,13 +492,13 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
 #pragma unroll
             for (int k = 0; k < 32; ++k) v[k] = fmaf(wr[128 + k], g[2], fmaf(wr[64 + k], g[1], wr[k] * g[0]));
         }
-        { float t[32];
+        if (PARAMS) { float t[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) t[k] = v[k];
           atomicAdd(&gpart[OFF_B2 + 32 * q + lane], rs32(t, lane)); }
         TB_MARK(8);
         // ---- layer 2: wgrad (X = H1 from operand 1), then dgrad ----
-        tb_wgrad_layer(c, p, q, v,
+        if (PARAMS) tb_wgrad_layer(c, p, q, v,
             [&](uint32_t (&xh)[16], uint32_t (&xl)[16]) {
                 umma::tmem_ld16(c.lane_base + TB_OP1_HI + 16 * q, xh); umma::tmem_ld16(c.lane_base + TB_OP1_LO + 16 * q, xl);
                 umma::wait_ld();
@@ -507,13 +511,13 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
         tb_load32(c, TB_D + 32 * q, v);
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = ((mask1 >> k) & 1u) ? v[k] : 0.f;   // dZ1
-        { float t[32];
+        if (PARAMS) { float t[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) t[k] = v[k];
           atomicAdd(&gpart[OFF_B1 + 32 * q + lane], rs32(t, lane)); }
         TB_MARK(10);
         // ---- layer 1: wgrad (X = e, 64 slots: this thread owns slots [16q, 16q+16), recomputed here) ----
-        {
+        if (PARAMS) {
             uint8_t *z_hi = c.r1, *z_lo = c.r1 + 2 * HALF_BLK, *x_hi = c.r2, *x_lo = c.r2 + 2 * HALF_BLK;
             for (int half = 0; half < 2; ++half) {
                 if ((p >> 6) == half) {
@@ -562,7 +566,7 @@ __global__ void __launch_bounds__(TC_NT, 1) field_bwd_tc_kernel(FieldDev f, Src 
             tb_store_op32(c, TB_OP2_HI, TB_OP2_LO, q, v);                    // dZ1
             umma::wait_st();
             __syncthreads();                                                 // wgrad MMAs done (waited) -> region 1 reusable
-            tb_copy(c.r1, f.tc_img + IMG_W1_HI, 2 * IMG_BLOCK);
+            if (PARAMS) tb_copy(c.r1, f.tc_img + IMG_W1_HI, 2 * IMG_BLOCK);
             tb_round(c, [&]() { tb_issue_dgrad(c, c.r1, c.r1 + IMG_BLOCK, 64); });
             uint32_t r[16];
             umma::tmem_ld16(c.lane_base + TB_D + 16 * q, r);

@@ -97,12 +97,13 @@ __device__ __forceinline__ void red_add_f4(float* addr, float a, float b, float 
 
 // Backward of one level: scatter w * dy into grad (kernel_grid_backward) and, if WANT_DX,
 // return dL/dx contribution (kernel_grid_backward_input; needs the forward features).
-template <bool WANT_DX>
+// SCATTER = false: input gradient only (pose refinement: no parameter gradients wanted).
+template <bool WANT_DX, bool SCATTER = true>
 __device__ __forceinline__ void grid_level_bwd(const float x[3], float2 dy, const float2* __restrict__ grid2,
                                                float* __restrict__ grad, const LevelInfo& li, float dx[3]) {
     uint32_t idx[8]; float w8[8];
     grid_corners(x, li, idx, w8);
-    if (dy.x != 0.f || dy.y != 0.f) {
+    if (SCATTER && (dy.x != 0.f || dy.y != 0.f)) {
         // the two corners of an x-pair are neighbours in the table whenever their indices differ only in bit 0 (cell x even
         // on a hashed level, even linear index on a dense one; level offsets are multiples of 8): one 16-byte reduction
         // instead of two 8-byte ones -- the scatter is bound by reduction lanes per SM

@@ -214,3 +214,89 @@ MF_API int mf_ro_update(const float* fitness, const float* mean_sdf, const float
     MF_LAUNCH_CHECK();
     return MF_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Gradient pose refinement of tracking (mipsfusion.py:501-556): pose parameters, their gradient and Adam on the device.
+// ---------------------------------------------------------------------------------------------
+__global__ void pose_to_c2w_kernel(const float* __restrict__ state, float* __restrict__ c2w) {
+    if (threadIdx.x != 0) return;
+    float q[4] = {state[0], state[1], state[2], state[3]}, m[9];
+    quat_to_mat(q, m);                                                   // qt_to_transform_matrix, geometry_helper.py:11-17
+    for (int r = 0; r < 3; ++r) {
+        for (int k = 0; k < 3; ++k) c2w[r * 4 + k] = m[r * 3 + k];
+        c2w[r * 4 + 3] = state[4 + r];
+    }
+    c2w[12] = 0.f; c2w[13] = 0.f; c2w[14] = 0.f; c2w[15] = 1.f;
+}
+
+__global__ void pose_refine_update_kernel(float* __restrict__ st, const float* __restrict__ c2w, const float* __restrict__ d_c2w,
+                                          const float* __restrict__ losses, const float* __restrict__ loss_w, float lr_rot,
+                                          float lr_trans, int wait_iters, float* __restrict__ best_c2w) {
+    if (threadIdx.x != 0) return;
+    if (st[24] != 0.f) return;                                           // the reference has left the loop (:551-552)
+    // get_loss_from_ret (mipsfusion.py:141-152): weighted sum in the reference's order rgb, depth, sdf, fs
+    float loss = 0.f;
+    loss += loss_w[0] * losses[0];
+    loss += loss_w[1] * losses[1];
+    loss += loss_w[2] * losses[2];
+    loss += loss_w[3] * losses[3];
+    if (st[22] < 0.f) {                                                  // first iteration: best = this pose (:540-542)
+        st[22] = loss;
+        for (int k = 0; k < 16; ++k) best_c2w[k] = c2w[k];
+    }
+    if (loss < st[22]) {                                                 // (:546-550)
+        st[22] = loss;
+        for (int k = 0; k < 16; ++k) best_c2w[k] = c2w[k];
+        st[23] = 0.f;
+    } else {
+        st[23] += 1.f;
+    }
+    if (st[23] > (float)wait_iters) { st[24] = 1.f; return; }            // break before backward / step
+    // ---- backward of qt_to_transform_matrix: d loss / d quaternion, d loss / d translation ----
+    const float r = st[0], i = st[1], j = st[2], k = st[3];
+    const float n2 = ((r * r + i * i) + j * j) + k * k, s = 2.0f / n2;
+    float G[9];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) G[a * 3 + b] = d_c2w[a * 4 + b];
+    // M = I + s * Q(q);  dM/dq_x = s * dQ/dq_x + Q * ds/dq_x,  ds/dq_x = -2 s q_x / n2 = -s^2 q_x
+    const float Q[9] = {-(j * j + k * k), i * j - k * r, i * k + j * r, i * j + k * r, -(i * i + k * k), j * k - i * r,
+                        i * k - j * r, j * k + i * r, -(i * i + j * j)};
+    float gq_dot = 0.f;
+    for (int t = 0; t < 9; ++t) gq_dot += G[t] * Q[t];
+    const float dQr[9] = {0, -k, j, k, 0, -i, -j, i, 0};
+    const float dQi[9] = {0, j, k, j, -2 * i, -r, k, r, -2 * i};
+    const float dQj[9] = {-2 * j, i, r, i, 0, k, -r, k, -2 * j};
+    const float dQk[9] = {-2 * k, -r, i, r, -2 * k, j, i, j, 0};
+    float g[7] = {0, 0, 0, 0, d_c2w[3], d_c2w[7], d_c2w[11]};
+    for (int t = 0; t < 9; ++t) { g[0] += G[t] * dQr[t]; g[1] += G[t] * dQi[t]; g[2] += G[t] * dQj[t]; g[3] += G[t] * dQk[t]; }
+    const float qv[4] = {r, i, j, k};
+    for (int t = 0; t < 4; ++t) g[t] = s * g[t] - s * s * qv[t] * gq_dot;
+    // ---- torch.optim.Adam (betas 0.9, 0.999, eps 1e-8, no weight decay), groups: quaternion lr_rot, translation lr_trans ----
+    const float step = st[21] + 1.f;
+    st[21] = step;
+    const float bc1 = 1.f - powf(0.9f, step), bc2 = 1.f - powf(0.999f, step);
+    for (int t = 0; t < 7; ++t) {
+        float m = st[7 + t], v = st[14 + t];
+        m = 0.9f * m + 0.1f * g[t];
+        v = 0.999f * v + 0.001f * g[t] * g[t];
+        st[7 + t] = m; st[14 + t] = v;
+        const float lr = t < 4 ? lr_rot : lr_trans;
+        st[t] -= (lr / bc1) * m / (sqrtf(v) / sqrtf(bc2) + 1e-8f);
+    }
+}
+
+MF_API int mf_pose_to_c2w(const float* state, float* c2w, void* stream) {
+    MF_CHECK_ARG(state && c2w);
+    pose_to_c2w_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(state, c2w);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}
+
+MF_API int mf_pose_refine_update(float* state, const float* c2w, const float* d_c2w, const float* losses, const float* loss_w,
+                                 double lr_rot, double lr_trans, int wait_iters, float* best_c2w, void* stream) {
+    MF_CHECK_ARG(state && c2w && d_c2w && losses && loss_w && best_c2w);
+    pose_refine_update_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(state, c2w, d_c2w, losses, loss_w, (float)lr_rot, (float)lr_trans,
+                                                                 wait_iters, best_c2w);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}

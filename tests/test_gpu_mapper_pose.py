@@ -100,3 +100,55 @@ def test_module_sees_stepped_decoder_after_mapping_steps():
     with torch.no_grad():
         out3 = model.run_network(pts).cpu()
     assert H.rel_err(out3, out0.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("wait_iters,backward", [(100, "fp32"), (2, "fp32"), (100, "tc")])
+def test_fused_pose_refinement_vs_oracle_loop(wait_iters, backward):
+    """FusedPoseRefiner (the GO loop of mipsfusion.py:501-556 without autograd) against the oracle's restatement of the loop
+    (autograd + torch.optim.Adam on quaternion / translation): per-iteration bookkeeping, best pose, pose after 10 iterations."""
+    import mipsfusion_b200 as mf
+    from mipsfusion_b200 import synth
+    from oracle import tracking as otrk
+    cfg = H.make_config(16, n_samples_d=50, n_range_d=25)
+    cfg["training"]["perturb"] = 0
+    cfg["tracking"] = {"lr_rot": 1e-3, "lr_trans": 1e-3, "wait_iters": wait_iters, "best": True}
+    of = H.oracle_field(cfg, grid_scale=0.3, seed=13)
+    model = H.cuda_model(cfg, H.state_of(of))
+    R = 500
+    rays7, _, poses, _ = H.synth_batch_packed(R, seed=31)
+    c2w = poses[0].clone()
+    # perturb the start pose a little (what RandomOptimizer leaves for the gradient stage)
+    d = torch.eye(4); d[:3, 3] = torch.tensor([0.01, -0.008, 0.006])
+    ang = 0.01
+    d[:3, :3] = torch.tensor([[1.0, -ang, 0.0], [ang, 1.0, 0.0], [0.0, 0.0, 1.0]]) / (1 + ang * ang) ** 0.5
+    d[2, 2] = 1.0
+    start = c2w @ d
+    ref_pose, ref_losses, ref_seen = otrk.refine_pose(of, start, rays7[:, :3], rays7[:, 3:6], rays7[:, 6:7], 10, wait_iters=wait_iters)
+    ref = mf.FusedPoseRefiner(model, backward=backward)
+    pose, state = ref.refine(start, rays7[:, :3].cuda(), rays7[:, 3:6].cuda(), rays7[:, 6].cuda(), 10)
+    torch.cuda.synchronize()
+    from mipsfusion_b200 import _lib as L
+    assert L.lib().mf_tc_check_error() == 0
+    st = state.cpu().numpy()
+    n_done = len(ref_losses)                                      # the oracle leaves the loop early when wait_iters is exceeded
+    assert int(st[21]) == (n_done if n_done == 10 else n_done - 1), (st[21], n_done)     # Adam steps taken
+    assert bool(st[24]) == (n_done < 10)
+    np.testing.assert_allclose(float(st[22]), min(ref_losses), rtol=1e-3)                 # best loss
+    err = np.abs(pose.cpu().numpy() - ref_pose.numpy()).max()
+    print(f"\n  pose refinement ({backward}, wait_iters {wait_iters}): {n_done} iterations, best-pose max abs diff {err:.2e}, losses {ref_losses[0]:.4f} -> {min(ref_losses):.4f}")
+    # Adam's step is lr * m / sqrt(v): where a pose component's gradient changes sign during the 10 iterations (the quaternion's
+    # real part does, on this fixture, between iterations 3 and 4: scripts/dbg_go.py) the step direction hangs on the last digits of
+    # the gradient, and any two fp32 implementations drift apart geometrically from there -- the fp32 backward (gradients 5e-7 from
+    # the oracle) and the tensor-core one (2.4e-4) end equally far from the oracle: 2.2e-4 / 2.8e-4 after 10 iterations.  So: the
+    # north_star's 1e-4 on the pose is asserted where the comparison is well conditioned (3 iterations: measured 6e-6), and the
+    # full 10 iterations are bounded at 5e-4 (half a single Adam step of lr = 1e-3).
+    assert err < 5e-4, err
+    ref3_pose, _, _ = otrk.refine_pose(of, start, rays7[:, :3], rays7[:, 3:6], rays7[:, 6:7], 3, wait_iters=wait_iters, best=False)
+    p3, _ = mf.FusedPoseRefiner(model, use_best=False, backward=backward).refine(start, rays7[:, :3].cuda(), rays7[:, 3:6].cuda(), rays7[:, 6].cuda(), 3)
+    err3 = np.abs(p3.cpu().numpy() - ref3_pose.numpy()).max()
+    assert err3 < 2e-5, err3
+    # and the last pose (use_best = False) follows the oracle's parameters as well
+    ref2 = mf.FusedPoseRefiner(model, use_best=False, backward=backward)
+    last, _ = ref2.refine(start, rays7[:, :3].cuda(), rays7[:, 3:6].cuda(), rays7[:, 6].cuda(), 10)
+    ref_last, _, _ = otrk.refine_pose(of, start, rays7[:, :3], rays7[:, 3:6], rays7[:, 6:7], 10, wait_iters=wait_iters, best=False)
+    assert np.abs(last.cpu().numpy() - ref_last.numpy()).max() < 5e-4

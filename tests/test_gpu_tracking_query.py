@@ -197,3 +197,27 @@ def test_joint_query_vs_oracle():
     # no submap sees the point -> -1 / masked
     far = jq.query(points=np.array([[50.0, 50.0, 50.0]]))
     assert float(far["sdf"][0]) == -1.0 and not bool(far["mask"][0])
+
+
+def test_render_full_img_vs_oracle():
+    """Logger.render_full_img (Logger.py:193-214): whole-image rendering on the device vs the oracle's render_rays on the same
+    rays (a 46 x 62 image keeps the oracle in seconds), one call and batched."""
+    import mipsfusion_b200 as mf
+    from mipsfusion_b200 import synth
+    cfg = H.make_config(14)
+    cfg["training"]["perturb"] = 0
+    of = H.oracle_field(cfg, grid_scale=0.3, seed=9)
+    model = H.cuda_model(cfg, H.state_of(of), train=False)
+    dirs = synth.camera_rays()[::10, ::10].contiguous()                 # (46, 62, 3)
+    c2w = synth.trajectory(4)[2]
+    frame = synth.render_frame(c2w, dirs)
+    rgb, depth = mf.render_full_img(model, dirs, c2w, frame["depth"])
+    rgb_b, depth_b = mf.render_full_img(model, dirs, c2w, frame["depth"], ray_batch_size=1000)
+    assert rgb.shape == (46, 62, 3) and depth.shape == (46, 62)
+    assert torch.equal(rgb, rgb_b) and torch.equal(depth, depth_b)
+    rays_d = torch.sum(dirs.reshape(-1, 1, 3) * c2w[None, :3, :3], -1)
+    rays_o = c2w[None, :3, 3].repeat(rays_d.shape[0], 1)
+    with torch.no_grad():
+        ret = of.render_rays(rays_o, rays_d, target_d=frame["depth"].reshape(-1, 1))
+    np.testing.assert_allclose(rgb.reshape(-1, 3).cpu().numpy(), ret["rgb"].numpy(), rtol=0, atol=1e-4)
+    np.testing.assert_allclose(depth.reshape(-1).cpu().numpy(), ret["depth"].numpy(), rtol=1e-4, atol=1e-4)
