@@ -739,8 +739,9 @@ def joint_query_bench(dev, res=512, n_submaps=16, group=None, shard="points", pr
 def frame_bench(dev, frames=3):
     """ms/frame of the reference's per-frame work at its shipped sizes (configs/FastCaMo-synth/FastCaMo-synth.yaml):
     RandomOptimizer 5 iterations x 2000 particles x 384 pixels, 10 gradient pose-refinement iterations x 1000 rays x 75
-    samples (pose gradients -> fp32 decoder route), and 15 mapping iterations x 2600 rays x 75 samples every 3rd frame
-    (amortised), on one synthetic 640x480 frame (cropped to 620x460)."""
+    samples, and 15 mapping iterations x 2600 rays x 75 samples every 3rd frame (amortised), on one synthetic 640x480 frame
+    (cropped to 620x460).  Pose refinement: FusedPoseRefiner (the GO loop without autograd; the drop-in autograd route is timed
+    beside it as ms_per_frame_640x480_autograd_go)."""
     import types
     import torch
     import helpers as H
@@ -750,7 +751,7 @@ def frame_bench(dev, frames=3):
     from mipsfusion_b200 import sampling_helper as sh
     cfg = H.make_config(HASH, n_samples_d=50, n_range_d=25)
     cfg["tracking"] = {"RO": {"particle_size": 2000, "initial_scaling_factor": 0.02, "rescaling_factor": 0.5, "n_rows": 16, "n_cols": 24},
-                       "ignore_edge_W": 20, "ignore_edge_H": 20}
+                       "ignore_edge_W": 20, "ignore_edge_H": 20, "lr_rot": 1e-3, "lr_trans": 1e-3, "wait_iters": 100, "best": True}
     of = H.oracle_field(cfg)
     model = H.cuda_model(cfg, H.state_of(of))
     dirs = synth.camera_rays()
@@ -760,41 +761,61 @@ def frame_bench(dev, frames=3):
     ds = types.SimpleNamespace(H=460, W=620, fx=320.0, fy=320.0, cx=309.5, cy=229.5, rays_d=dirs)
     ro = mf.RandomOptimizer(cfg, types.SimpleNamespace(dataset=ds, device=str(dev)))
     mapper = FusedMapper(model)
+    refiner = mf.FusedPoseRefiner(model)
     tw = cfg["training"]
 
-    def one_frame(do_map):
+    def one_frame(do_map, fused_go=True):
         model.eval()
         pose = ro.optimize(model, frame["depth"], c2w.clone(), c2w.clone(), n_iter=5).to(dev)      # RO (returns a CPU pose, as the reference)
         model.train()
         rows, cols = sh.sample_pixels_mix(460, 620, 16, 24, depth_d, 1000)
         d_cam, t_rgb, t_d = dirs_d[rows, cols], rgb_d[rows, cols], depth_d[rows, cols].unsqueeze(-1)
-        trans = pose[:3, 3].clone().requires_grad_(True)
-        rot = pose[:3, :3].clone().requires_grad_(True)
-        opt = torch.optim.Adam([rot, trans], lr=1e-3)
-        for _ in range(10):                                                                       # GO (mipsfusion.py:501-556)
-            opt.zero_grad()
-            rays_o = trans[None, :].repeat(1000, 1)
-            rays_d = torch.sum(d_cam[..., None, :] * rot[None], -1)
-            ret = model(rays_o, rays_d, t_rgb, t_d, EMD_w=0.0)
-            loss = tw["rgb_weight"] * ret["rgb_loss"] + tw["sdf_weight"] * ret["sdf_loss"] + tw["fs_weight"] * ret["fs_loss"]
-            loss.backward()
-            opt.step()
+        if fused_go:
+            pose_f, _ = refiner.refine(pose, d_cam, t_rgb, t_d, 10)                               # GO (mipsfusion.py:501-556)
+            pose = pose_f.clone()
+        else:
+            trans = pose[:3, 3].clone().requires_grad_(True)
+            rot = pose[:3, :3].clone().requires_grad_(True)
+            opt = torch.optim.Adam([rot, trans], lr=1e-3)
+            for _ in range(10):
+                opt.zero_grad()
+                rays_o = trans[None, :].repeat(1000, 1)
+                rays_d = torch.sum(d_cam[..., None, :] * rot[None], -1)
+                ret = model(rays_o, rays_d, t_rgb, t_d, EMD_w=0.0)
+                loss = tw["rgb_weight"] * ret["rgb_loss"] + tw["sdf_weight"] * ret["sdf_loss"] + tw["fs_weight"] * ret["fs_loss"]
+                loss.backward()
+                opt.step()
         if do_map:
             idx = torch.randint(0, 460 * 620, (2600,), device=dev)
             r_, c_ = idx // 620, idx % 620
             ro_, rd_ = pose[None, :3, 3].repeat(2600, 1).contiguous(), torch.sum(dirs_d[r_, c_][..., None, :] * pose[None, :3, :3], -1).contiguous()
             for _ in range(15):                                                                   # local BA (mipsfusion.py:293-335)
                 mapper.step(ro_, rd_, rgb_d[r_, c_].contiguous(), depth_d[r_, c_].contiguous())
-        return float(loss.detach())
-    one_frame(True)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for k in range(frames):
-        one_frame(k % 3 == 0)
-    torch.cuda.synchronize()
-    ms = (time.perf_counter() - t0) / frames * 1e3
-    return {"ms_per_frame_640x480": ms,
-            "frame_shape": "RO 5 x 2000 x 384, pose refinement 10 x 1000 rays x 75 (fp32 decoder route), mapping 15 x 2600 rays x 75 every 3rd frame"}
+        return float(pose[0, 3])                                                                  # the frame's pose is read on the host
+
+    out = {}
+    for fused, key in ((True, "ms_per_frame_640x480"), (False, "ms_per_frame_640x480_autograd_go")):
+        one_frame(True, fused)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(frames):
+            one_frame(k % 3 == 0, fused)
+        torch.cuda.synchronize()
+        out[key] = (time.perf_counter() - t0) / frames * 1e3
+    # the pose-refinement stage alone, device time
+    rows, cols = sh.sample_pixels_mix(460, 620, 16, 24, depth_d, 1000)
+    d_cam, t_rgb, t_d = dirs_d[rows, cols], rgb_d[rows, cols], depth_d[rows, cols].unsqueeze(-1)
+    pose0 = c2w.to(dev)
+    refiner.refine(pose0, d_cam, t_rgb, t_d, 10)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); a.record()
+    for _ in range(3):
+        refiner.refine(pose0, d_cam, t_rgb, t_d, 10)
+    b.record(); torch.cuda.synchronize()
+    out["pose_refinement_10_iterations_ms"] = a.elapsed_time(b) / 3
+    out["frame_shape"] = ("RO 5 x 2000 x 384, pose refinement 10 x 1000 rays x 75 (FusedPoseRefiner: tensor-core forward + ray-gradient-only "
+                          "tensor-core backward, no autograd), mapping 15 x 2600 rays x 75 every 3rd frame")
+    return out
 
 
 if __name__ == "__main__":

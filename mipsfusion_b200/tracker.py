@@ -68,7 +68,7 @@ class FusedPoseRefiner:
     def refine(self, c2w_init, rays_d_cam, target_rgb, target_d, n_iter, u=None, EMD_w=0.0):
         """c2w_init (4,4); rays_d_cam (N,3) camera-frame directions, target_rgb (N,3), target_d (N,) or (N,1): device tensors of
         the pixels sampled once for the whole loop (:512-522).  u: optional (n_iter, N, S) stratified-jitter draws.
-        -> (c2w (4,4) device tensor: the best pose if ``use_best`` else the last one, state tensor).  No synchronisation."""
+        -> (c2w (4,4) device tensor: the best pose if ``use_best`` else the reference's `c2w_est`, state tensor).  No synchronisation."""
         model, dev = self.model, self.dev
         R = rays_d_cam.shape[0]
         cfg, lins = model._render_cfg(True, EMD_w, dev)
@@ -112,5 +112,8 @@ class FusedPoseRefiner:
             self.launches += 15
         if self.use_best and n_iter > 0:
             return b["best"], b["state"]
-        L.call("mf_pose_to_c2w", L.ptr(b["state"]), L.ptr(b["c2w"]), st)
+        # tracking.best = False: the reference hands back `c2w_est`, the matrix it formed at the START of the last executed
+        # iteration (mipsfusion.py:544,562-563) -- the last Adam step is never evaluated.  b["c2w"] holds exactly that matrix.
+        if n_iter <= 0:
+            L.call("mf_pose_to_c2w", L.ptr(b["state"]), L.ptr(b["c2w"]), st)
         return b["c2w"][0], b["state"]

@@ -1,6 +1,8 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -8
-python bench.py --steps 20 --warmup 5 > gpurun_out/r2b_bench.json 2> gpurun_out/r2b_bench.err; echo "bench rc=$?"
-python -c "
-import json; d=json.load(open('gpurun_out/r2b_bench.json'))
-print({k:d[k] for k in ('value','ms_per_step')}); print(d['roofline']['phase_ms']); print(d['roofline']['ms_per_launch'], d['roofline']['frac']); print(d['e2e']['value'], d['also']['e2e_autograd_api_rays_per_s'], d['also']['tracking_pose_candidates_per_s'], d['also']['ms_per_frame_640x480'])"
-timeout 300 python scripts/prof_e2e.py 2>&1 | head -60
+python -m pytest tests/test_gpu_mapper_pose.py -q -k refinement 2>&1 | tail -3
+python - <<'PY'
+import sys, torch, json
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+import bench
+print(json.dumps(bench.frame_bench(torch.device('cuda', 0)), indent=1))
+print(json.dumps({k: v for k, v in bench.render_full_bench(torch.device('cuda', 0)).items() if not k.startswith('_')}, indent=1))
+PY

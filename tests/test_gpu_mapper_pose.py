@@ -102,7 +102,7 @@ def test_module_sees_stepped_decoder_after_mapping_steps():
     assert H.rel_err(out3, out0.cpu()) < 1e-5
 
 
-@pytest.mark.parametrize("wait_iters,backward", [(100, "fp32"), (2, "fp32"), (100, "tc")])
+@pytest.mark.parametrize("wait_iters,backward", [(100, "fp32"), (0, "fp32"), (100, "tc")])
 def test_fused_pose_refinement_vs_oracle_loop(wait_iters, backward):
     """FusedPoseRefiner (the GO loop of mipsfusion.py:501-556 without autograd) against the oracle's restatement of the loop
     (autograd + torch.optim.Adam on quaternion / translation): per-iteration bookkeeping, best pose, pose after 10 iterations."""
