@@ -40,24 +40,25 @@ struct T3Cons {
     bool ok;
 };
 
-// one decoder layer on the consumer side; a_col(ks, lo) = tensor-memory column (relative to the allocation) of k-step ks
-template <int N_OUT = 128, class ColFn, class AfterFn>
-__device__ __forceinline__ void t3_run_layer(T3Cons& c, int img_hi, int img_lo, int KS, ColFn a_col, AfterFn after_issue) {
+// one decoder layer on the consumer side; a_col(ks, lo) = tensor-memory column (relative to the allocation) of k-step ks.
+// The issue loop is fully unrolled and the weight descriptors are one base descriptor plus constants (start-address field in
+// 16-byte units): the 255 other consumer threads wait while thread 0 issues, so its instruction count is on the tile's critical path.
+template <int KS, int N_OUT = 128, class ColFn, class AfterFn>
+__device__ __forceinline__ void t3_run_layer(T3Cons& c, int img_hi, int img_lo, ColFn a_col, AfterFn after_issue) {
     umma::wait_st();
     umma::fence_before_sync();
     t3_cons_sync();
     if (c.tid == 0) {
         umma::fence_after_sync();
         constexpr uint32_t idesc = umma::idesc_bf16(128, N_OUT, 0, 0);     // N_OUT < 128: only the first N_OUT output features
-        const uint32_t w_hi = umma::smem_u32(c.img + img_hi), w_lo = umma::smem_u32(c.img + img_lo);
-        uint32_t acc = 0;
-#pragma unroll 1
+        const uint64_t dh = umma::smem_desc_sw128(umma::smem_u32(c.img + img_hi), 16, 1024);
+        const uint64_t dl = umma::smem_desc_sw128(umma::smem_u32(c.img + img_lo), 16, 1024);
+#pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
-#pragma unroll 1
+#pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
-                const uint32_t wb = (pass == 1 ? w_lo : w_hi) + (uint32_t)((ks >> 2) * IMG_BLOCK + (ks & 3) * 32);
-                umma::mma_ts(c.tmem + T3_D, c.tmem + (uint32_t)a_col(ks, pass == 2), umma::smem_desc_sw128(wb, 16, 1024), idesc, acc);
-                acc = 1;
+                const uint32_t off = (uint32_t)(((ks >> 2) * IMG_BLOCK + (ks & 3) * 32) >> 4);
+                umma::mma_ts(c.tmem + T3_D, c.tmem + (uint32_t)a_col(ks, pass == 2), (pass == 1 ? dl : dh) + off, idesc, (pass | ks) ? 1u : 0u);
             }
         }
         umma::commit(c.bar);
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(2 * T3_GT, 1) field_fwd_tc3_kernel(FieldDev f,
                 for (int ch = 0; ch < 3; ++ch) rgb_e[ch] = cpart[ch * TC_LD + p] + cpart[(3 + ch) * TC_LD + p];
             }
             // ---- pts_linear.0 + ReLU (A = staged e) ----
-            t3_run_layer(c, IMG_W1_HI, IMG_W1_LO, 4, [stg](int ks, bool lo) { return stg + (lo ? T3_E_LO : T3_E_HI) + 8 * ks; }, []() {});
+            t3_run_layer<4>(c, IMG_W1_HI, IMG_W1_LO, [stg](int ks, bool lo) { return stg + (lo ? T3_E_LO : T3_E_HI) + 8 * ks; }, []() {});
             T3_MARK(50);
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(2 * T3_GT, 1) field_fwd_tc3_kernel(FieldDev f,
             T3_MARK(51);
             // ---- pts_linear.2 (SDF only: just the 64 sdf_emb outputs, 32 per thread) ----
             if (SDF_ONLY) {
-                t3_run_layer<64>(c, IMG_W2_HI, IMG_W2_LO, 8, [](int ks, bool lo) { return (lo ? T3_A_LO : T3_A_HI) + 8 * ks; }, []() {});
+                t3_run_layer<8, 64>(c, IMG_W2_HI, IMG_W2_LO, [](int ks, bool lo) { return (lo ? T3_A_LO : T3_A_HI) + 8 * ks; }, []() {});
                 T3_MARK(52);
                 const int f0 = 32 * h;
                 t3_load32(c, T3_D + f0, v);
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(2 * T3_GT, 1) field_fwd_tc3_kernel(FieldDev f,
                 }
                 t3_store32(c, f0, v);
             } else {
-            t3_run_layer(c, IMG_W2_HI, IMG_W2_LO, 8, [](int ks, bool lo) { return (lo ? T3_A_LO : T3_A_HI) + 8 * ks; }, []() {});
+            t3_run_layer<8>(c, IMG_W2_HI, IMG_W2_LO, [](int ks, bool lo) { return (lo ? T3_A_LO : T3_A_HI) + 8 * ks; }, []() {});
             T3_MARK(52);
             {
                 float r[3] = {0.f, 0.f, 0.f};
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(2 * T3_GT, 1) field_fwd_tc3_kernel(FieldDev f,
             T3_MARK(53);
             // ---- sdf_linear.0 + ReLU (k-steps 0-3: sdf_emb, 4-5: staged grid features); releases the stage ----
             uint64_t* empty = bars + 3 + s;
-            t3_run_layer(c, IMG_W3_HI, IMG_W3_LO, 6,
+            t3_run_layer<6>(c, IMG_W3_HI, IMG_W3_LO,
                          [stg](int ks, bool lo) { return ks < 4 ? (lo ? T3_A_LO : T3_A_HI) + 8 * ks : stg + (lo ? T3_G_LO : T3_G_HI) + 8 * (ks - 4); },
                          [empty]() { umma::commit(empty); });
             T3_MARK(54);

@@ -18,17 +18,16 @@ if mode == "ro":
     print(bench.tracking_bench(model, cfg, dev, iters=iters))
 elif mode == "jq":
     print(bench.joint_query_bench(dev, res=128))
-elif mode == "go":
+elif mode == "go":                       # fused gradient pose refinement: ray-gradient-only tensor-core backward
+    import mipsfusion_b200 as mf
     cfg = H.make_config(bench.HASH, n_samples_d=50, n_range_d=25)
+    cfg["tracking"] = {"lr_rot": 1e-3, "lr_trans": 1e-3, "wait_iters": 100, "best": True}
     of = H.oracle_field(cfg); model = H.cuda_model(cfg, H.state_of(of))
-    rays_o, rays_d, rgb, d, u = [t.to(dev) for t in H.synth_batch(1000, 75, seed=2)]
-    tw = cfg["training"]
-    for _ in range(iters):
-        ro_, rd_ = rays_o.clone().requires_grad_(True), rays_d.clone().requires_grad_(True)
-        ret = model(ro_, rd_, rgb, d, EMD_w=0.0, u=u)
-        (tw["rgb_weight"] * ret["rgb_loss"] + tw["sdf_weight"] * ret["sdf_loss"] + tw["fs_weight"] * ret["fs_loss"]).backward()
+    rays7, _, poses, _ = H.synth_batch_packed(1000, seed=2)
+    ref = mf.FusedPoseRefiner(model)
+    pose, st = ref.refine(poses[0], rays7[:, :3].to(dev), rays7[:, 3:6].to(dev), rays7[:, 6].to(dev), iters)
     torch.cuda.synchronize()
-    print("go ok", float(ro_.grad.abs().sum()))
+    print("go ok", pose.cpu().numpy()[:3, 3])
 elif mode == "map":
     from mipsfusion_b200.mapper import FusedMapper
     cfg, of = bench.build_model()
