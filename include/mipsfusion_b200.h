@@ -83,7 +83,7 @@ int mf_set_decoder_impl(int impl);
 int mf_get_decoder_impl(void);
 /* 1 if a tensor-core kernel reported an MMA-completion timeout since the last call (clears the flag;
  * synchronises the device -- diagnostics only). */
-/* A/B switch of the tensor-core backward: 0 = role-split kernel (default), 1 = single-role kernel of round 1. */
+/* A/B switch of the tensor-core backward: 0 = three-role kernel (default), 1 = single-role kernel of round 1, 3 = four-role kernel (A/B only). */
 int mf_set_bwd_impl(int impl);
 int mf_tc_check_error(void);
 /* Diagnostics: out (128,128) = x (128,K) w (128,K)^T through one tcgen05 layer; K % 16 == 0, K <= 128;

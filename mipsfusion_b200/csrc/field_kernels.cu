@@ -5,6 +5,7 @@
 #include "field_tc_launch.cuh"
 #include "field_tc_bwd.cuh"
 #include "field_tc_bwd2.cuh"
+#include "field_tc_bwd3.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Weight re-layout (runs once per optimiser step; 36.6 k floats).
@@ -574,10 +575,15 @@ static int launch_field_bwd(const FieldDev& d, const Src& src, const float* d_ra
             MF_LAUNCH_CHECK();
             return MF_OK;
         }
-        if (!d_pts && mf_bwd_impl() == 0) {                // role-split kernel (parameter gradients only)
-            int rc = set_smem(field_bwd_tc2_kernel<Src>, b2::SMEM); if (rc) return rc;
+        if (!d_pts && mf_bwd_impl() != 1) {                // role-split kernels (parameter gradients only)
             uint32_t* cta_scr = reinterpret_cast<uint32_t*>(scratch + act_scratch_words(N));
-            field_bwd_tc2_kernel<Src><<<grid, b2::B2_NT, b2::SMEM, st>>>(d, src, d_raw, grad_grid, workspace, cta_scr, N, am, mf_tc_error_flag(), mf_tc_profile_buffer());
+            if (mf_bwd_impl() == 3 && d.feat) {            // four roles (A/B only: measured slower, field_tc_bwd3.cuh); needs the feature cache
+                int rc = set_smem(field_bwd_tc3_kernel<Src>, b3::SMEM); if (rc) return rc;
+                field_bwd_tc3_kernel<Src><<<grid, b3::B3_NT, b3::SMEM, st>>>(d, src, d_raw, grad_grid, workspace, cta_scr, N, am, mf_tc_error_flag(), mf_tc_profile_buffer());
+            } else {                                       // three roles (default)
+                int rc = set_smem(field_bwd_tc2_kernel<Src>, b2::SMEM); if (rc) return rc;
+                field_bwd_tc2_kernel<Src><<<grid, b2::B2_NT, b2::SMEM, st>>>(d, src, d_raw, grad_grid, workspace, cta_scr, N, am, mf_tc_error_flag(), mf_tc_profile_buffer());
+            }
             mf_ktimer_end(1, st);
             MF_LAUNCH_CHECK();
             reduce_partials_kernel<<<(MF_MLP_PARAMS + 31) / 32 + 1, 256, 0, st>>>(workspace, grid, grad_mlp, 2, d.prep);

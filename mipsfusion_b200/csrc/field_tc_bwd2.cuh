@@ -65,7 +65,7 @@ static_assert(SMEM <= 227 * 1024, "shared memory budget");
 constexpr int T_D = 0, T_R1_HI = 128, T_R1_LO = 192, T_R2_HI = 256, T_R2_LO = 320, T_DW = 384;
 constexpr int T_G_HI = T_R2_HI + 32, T_G_LO = T_R2_LO + 32;
 // ---- CTA-private scratch in global memory, uint32 [word][point] ----
-constexpr int SCR_H1 = 0, SCR_H3 = 128, SCR_RGB = 256, SCR_WORDS = 320;      // hi words first, then lo words, per region
+constexpr int SCR_H1 = 0, SCR_H3 = 128, SCR_RGB = 256, SCR_U = 320, SCR_WORDS = 328;     // hi words first, then lo words, per region (U: four-role kernel only)
 constexpr int64_t SCR_CTA_WORDS = (int64_t)SCR_WORDS * TC_TP;
 constexpr int REGS_CHAIN = 160, REGS_WGRAD = 88, REGS_SCATTER = 104;       // 256 x 160 + 128 x 88 + 128 x 104 = 65,536
 // ---- mbarriers ----
