@@ -14,15 +14,21 @@ PARAM_ORDER = ["pts_linear.0.weight", "pts_linear.0.bias", "pts_linear.2.weight"
 class _Workspace:
     """Per-device scratch for the per-CTA partial parameter gradients (never pickled)."""
     _bufs = {}
+    _sizes = {}                                      # (points, ray grads, extra) -> floats (the size functions are pure)
 
     @classmethod
     def get(cls, device, extra_floats=0, field_points=None, want_ray_grads=False):
         """field_points: size the buffer for a fused field backward over that many points
         (mf_field_bwd_workspace_size), otherwise for the stand-alone decoder backward."""
-        if field_points is not None:
-            n = int(L.lib().mf_field_bwd_workspace_size(int(field_points), int(bool(want_ray_grads))))
-        else:
-            n = int(L.lib().mf_mlp_grad_workspace_size()) + int(extra_floats)
+        skey = (field_points, bool(want_ray_grads), extra_floats)
+        n = cls._sizes.get(skey)
+        if n is None:
+            if field_points is not None:
+                n = int(L.lib().mf_field_bwd_workspace_size(int(field_points), int(bool(want_ray_grads))))
+            else:
+                n = int(L.lib().mf_mlp_grad_workspace_size()) + int(extra_floats)
+            if len(cls._sizes) < 256:
+                cls._sizes[skey] = n
         # one buffer per (device, stream): backward passes issued on different streams must not share scratch
         key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0)
         buf = cls._bufs.get(key)
@@ -96,7 +102,42 @@ class MLP_reg(nn.Module):
 
     def flat_weights(self):
         """The state_dict tensors concatenated in order (MF_MLP_PARAMS floats)."""
+        flat = self.flat_storage()
+        if flat is not None:
+            return flat[:L.MF_MLP_PARAMS]
         return torch.cat([p.detach().reshape(-1) for p in self.ordered_params()])
+
+    def flatten_parameters(self):
+        """Re-seat the ten parameters as views of ONE flat buffer in state_dict order (padded to a multiple of four floats:
+        the layout of the kernels' weight blob), so that the kernel-layout weights are rebuilt without a concatenation and a
+        fused optimiser steps the whole decoder in one launch (``create_map_optimizer``).  Values, shapes, ``state_dict``
+        and ``load_state_dict`` are unchanged; ``.to()`` / ``deepcopy`` give ordinary separate tensors again (and the slower
+        generic routes).  -> the flat buffer."""
+        ps = self.ordered_params()
+        dev = ps[0].device
+        if dev.type != "cuda":
+            raise L.MipsFusionB200Error("MLP_reg parameters must live on a CUDA device (no CPU fallback)")
+        flat = torch.zeros((L.MF_MLP_PARAMS + 3) // 4 * 4, device=dev, dtype=torch.float32)
+        o = 0
+        with torch.no_grad():
+            for p in ps:
+                n = p.numel()
+                flat[o:o + n].copy_(p.detach().reshape(-1))
+                p.data = flat[o:o + n].view(p.shape)
+                o += n
+        self.__dict__["_flat"] = (flat, tuple(p.data_ptr() for p in ps))
+        self.__dict__.pop("_prep_cache", None)
+        return flat
+
+    def flat_storage(self):
+        """The flat buffer of :meth:`flatten_parameters` while every parameter still is its view, else None."""
+        f = self.__dict__.get("_flat")
+        if f is None:
+            return None
+        if tuple(p.data_ptr() for p in self.ordered_params()) != f[1]:
+            self.__dict__.pop("_flat")
+            return None
+        return f[0]
 
     def prepared(self):
         """Kernel-layout weights, rebuilt only when a parameter changed (mf_mlp_prepare)."""
@@ -113,9 +154,22 @@ class MLP_reg(nn.Module):
                     owner._seen_versions = vers
                 return owner.prep
             self.__dict__.pop("_ext_prep")
+        flat = self.flat_storage()
+        if flat is not None:
+            # flat storage: the image is rebuilt IN PLACE (same buffer, so the cached field descriptor stays valid) whenever a
+            # parameter's version moved; FusedAdam does it right after its step (refresh_prepared)
+            key = tuple(p._version for p in ps)
+            cache = self.__dict__.get("_prep_cache")
+            if cache is None or cache[2] is not flat:
+                cache = [None, torch.empty(int(L.lib().mf_mlp_prep_size()), device=flat.device, dtype=torch.float32), flat]
+                self.__dict__["_prep_cache"] = cache
+            if cache[0] != key:
+                L.call("mf_mlp_prepare", L.ptr(flat), L.ptr(cache[1]), L.stream())
+                cache[0] = key
+            return cache[1]
         key = tuple((p.data_ptr(), p._version) for p in ps)
         cache = self.__dict__.get("_prep_cache")
-        if cache is None or cache[0] != key:
+        if cache is None or len(cache) != 2 or cache[0] != key:
             dev = ps[0].device
             if dev.type != "cuda":
                 raise L.MipsFusionB200Error("MLP_reg parameters must live on a CUDA device (no CPU fallback)")
@@ -131,6 +185,7 @@ class MLP_reg(nn.Module):
         s.pop("_prep_cache", None)
         s.pop("_ext_prep", None)
         s.pop("_flat_grad", None)
+        s.pop("_flat", None)
         s.pop("_ordered", None)
         return s
 
@@ -146,7 +201,7 @@ class MLP_reg(nn.Module):
         dev = ps[0].device
         flat = self.__dict__.get("_flat_grad")
         if flat is None or flat.device != dev:
-            flat = torch.zeros(L.MF_MLP_PARAMS, device=dev, dtype=torch.float32)
+            flat = torch.zeros((L.MF_MLP_PARAMS + 3) // 4 * 4, device=dev, dtype=torch.float32)     # padded: float4 optimiser kernels
             self.__dict__["_flat_grad"] = flat
         if all(p.grad is None for p in ps):
             flat.zero_()

@@ -95,9 +95,14 @@ def _grad_targets(model, grid, dev, need_grid, need_mlp):
     return g_grid, ret_grid, torch.zeros(L.MF_MLP_PARAMS, device=dev, dtype=torch.float32), True
 
 
+_ZERO = {}                                      # device -> cached 0-dim zero (stand-in for an undefined loss gradient)
+
+
 class _RenderFn(torch.autograd.Function):
     """render_rays (+ losses when targets are given).  Outputs:
-    rgb (R,3), depth (R), aux (R,3)=[depth_var, disp, acc], z (R,S), raw (R,S,10), losses (8)."""
+    rgb (R,3), depth (R), aux (R,3)=[depth_var, disp, acc], z (R,S), raw (R,S,10), counts (2), then the scalars rgb_loss,
+    depth_loss, sdf_loss, fs_loss, psnr (views of one 8-float buffer the loss kernel fills: separate outputs, so that the
+    caller's weighted sum back-propagates four scalars instead of three select-backward nodes with a zero-fill each)."""
 
     @staticmethod
     def forward(ctx, rays_o, rays_d, target_rgb, target_d, u, emd_w, model, grid, *mlp_params):
@@ -127,7 +132,8 @@ class _RenderFn(torch.autograd.Function):
         rgb = torch.empty(R, 3, device=dev, dtype=torch.float32)
         depth = torch.empty(R, device=dev, dtype=torch.float32)
         aux = torch.empty(R, 3, device=dev, dtype=torch.float32)
-        losses = torch.zeros(8, device=dev, dtype=torch.float32)
+        # (the loss kernels write all eight entries when targets are given)
+        losses = torch.empty(8, device=dev, dtype=torch.float32) if target_d is not None else torch.zeros(8, device=dev, dtype=torch.float32)
         scratch = torch.empty(R * 8, device=dev, dtype=torch.float32) if target_d is not None else None
         L.call("mf_render_loss_fwd", L.ptr(raw), L.ptr(z), L.ptr(target_rgb), L.ptr(target_d), L.ptr(counts), C.byref(cfg),
                L.ptr(rgb), L.ptr(depth), L.ptr(aux), None, None, L.ptr(losses), L.ptr(scratch), R, S, st)
@@ -136,19 +142,25 @@ class _RenderFn(torch.autograd.Function):
         ctx.has_t = target_d is not None
         ctx.save_for_backward(rays_o, rays_d, target_rgb, target_d, z, raw, counts, losses, grid)
         ctx.shapes = [p.shape for p in mlp_params]
-        ctx.mark_non_differentiable(aux, z, counts)
+        l_rgb, l_depth, l_sdf, l_fs, psnr = losses[0], losses[1], losses[2], losses[3], losses[4]
+        ctx.mark_non_differentiable(aux, z, counts, psnr)
         ctx.set_materialize_grads(False)          # unused outputs arrive as None in backward (no dense zero buffers)
-        return rgb, depth, aux, z, raw, losses, counts
+        return rgb, depth, aux, z, raw, counts, l_rgb, l_depth, l_sdf, l_fs, psnr
 
     @staticmethod
-    def backward(ctx, g_rgb, g_depth, g_aux, g_z, g_raw, g_losses, g_counts):
+    def backward(ctx, g_rgb, g_depth, g_aux, g_z, g_raw, g_counts, g_l0, g_l1, g_l2, g_l3, g_psnr):
         rays_o, rays_d, target_rgb, target_d, z, raw, counts, losses, grid = ctx.saved_tensors
         model, cfg, S = ctx.model, ctx.cfg, ctx.S
         dev, R = rays_o.device, rays_o.shape[0]
         st = L.stream()
         field = model._field(ctx.keep, impl=ctx.impl)
         d_raw = torch.empty_like(raw)
-        gl = g_losses[:4].contiguous() if g_losses is not None else None
+        gl = None
+        if not (g_l0 is None and g_l1 is None and g_l2 is None and g_l3 is None):
+            zero = _ZERO.get(dev)
+            if zero is None:
+                zero = _ZERO[dev] = torch.zeros((), device=dev, dtype=torch.float32)
+            gl = torch.stack([zero if g is None else g.reshape(()) for g in (g_l0, g_l1, g_l2, g_l3)]).to(torch.float32)
         g_rgb = g_rgb.contiguous() if g_rgb is not None else None
         g_depth = g_depth.contiguous() if g_depth is not None else None
         L.call("mf_render_loss_bwd", L.ptr(raw), L.ptr(z), L.ptr(target_rgb), L.ptr(target_d), L.ptr(counts), L.ptr(losses),
@@ -324,7 +336,7 @@ class JointEncoding(nn.Module):
                                *self.decoder.ordered_params())
 
     def render_rays(self, rays_o, rays_d, target_d=None, u=None):
-        rgb, depth, aux, z, raw, _, _ = self._render(rays_o, rays_d, None, target_d, u, 0.0)
+        rgb, depth, aux, z, raw = self._render(rays_o, rays_d, None, target_d, u, 0.0)[:5]
         return {"rgb": rgb, "depth": depth, "disp_map": aux[:, 1], "acc_map": aux[:, 2], "depth_var": aux[:, 0],
                 "z_vals": z, "raw": raw}
 
@@ -358,6 +370,6 @@ class JointEncoding(nn.Module):
     def forward(self, rays_o, rays_d, target_rgb, target_d, EMD_w=0.01, u=None):
         if not self.training:
             return self.render_rays(rays_o, rays_d, target_d=target_d, u=u)
-        rgb, depth, aux, z, raw, losses, counts = self._render(rays_o, rays_d, target_rgb, target_d, u, EMD_w)
-        return {"rgb": rgb, "depth": depth, "rgb_loss": losses[0], "depth_loss": losses[1], "sdf_loss": losses[2],
-                "fs_loss": losses[3], "psnr": losses[4].detach()}
+        out = self._render(rays_o, rays_d, target_rgb, target_d, u, EMD_w)
+        return {"rgb": out[0], "depth": out[1], "rgb_loss": out[6], "depth_loss": out[7], "sdf_loss": out[8],
+                "fs_loss": out[9], "psnr": out[10]}
