@@ -329,9 +329,9 @@ def run_gpu(args):
     step_ms = dev_ms / args.steps
     step_bytes = 2 * ALG_BYTES_PER_POINT * P + ADAM_BYTES_PER_PARAM * n_params + (28 + 4 * S + 44) * R_RAYS     # 651.3 MB
     traffic = ncu_traffic()
-    roof = {"bound": "hbm", "kernel": "field_bwd_tc_kernel (tcgen05 recompute-forward + dgrad + wgrad + grid scatter)",
+    roof = {"bound": "hbm", "kernel": "field_bwd_tc2_kernel (role-split tcgen05 backward: recompute-forward + dgrad chain | wgrad read-out | grid scatter)",
             "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-            "traffic": traffic.get("field_bwd_tc_kernel"), "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum, "
+            "traffic": traffic.get("field_bwd_tc2_kernel"), "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum, "
             "ncu --set full, profiles/r2_ncu_traffic.json)", "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
             "ms_per_launch": bwd_ms, "alg_bytes_per_launch": alg_bytes, "alg_bytes_per_point": ALG_BYTES_PER_POINT,
             "points_per_launch": P, "active_points_per_launch": n_active,

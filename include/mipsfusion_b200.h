@@ -85,6 +85,8 @@ int mf_get_decoder_impl(void);
  * synchronises the device -- diagnostics only). */
 /* A/B switch of the tensor-core backward: 0 = three-role kernel (default), 1 = single-role kernel of round 1, 3 = four-role kernel (A/B only). */
 int mf_set_bwd_impl(int impl);
+/* A/B switch of the forward kernel's tile scheduling: 1 = dynamic (global tile counter, default), 0 = static striding. */
+int mf_set_dynamic_tiles(int on);
 int mf_tc_check_error(void);
 /* Diagnostics: out (128,128) = x (128,K) w (128,K)^T through one tcgen05 layer; K % 16 == 0, K <= 128;
  * passes = 1 (bf16) or 3 (bf16x3 split). */
@@ -97,6 +99,9 @@ int mf_debug_umma_wgrad(const float* dz, const float* x, float* out, int Kf, int
 
 /* Diagnostics: switch the in-kernel clock stamps of the tensor-core backward on/off and read the last ones. */
 int mf_debug_profile(int on, long long* out_host);
+/* All stamps (n <= 1024 int64): [0,64) as above; [64+2b, 65+2b] / [576+2b, 577+2b] = %globaltimer (ns) at the start / end of
+ * CTA b of the last profiled forward / backward tensor-core kernel.  Diagnostics only. */
+int mf_debug_profile_all(long long* out_host, int n);
 /* Diagnostics for bench.py's roofline line: when on, the launchers bracket the dominant kernel itself with a CUDA event pair
  * on the launching stream (slot 0 field forward, 1 field backward, 2 RandomOptimizer field query, 3 joint-query field query);
  * mf_debug_kernel_ms waits for the last bracketed launch of `slot` and returns its duration. */

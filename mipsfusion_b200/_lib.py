@@ -56,11 +56,13 @@ PROTOTYPES = {
     "mf_set_decoder_impl": (_I, [_I]),
     "mf_get_decoder_impl": (_I, []),
     "mf_set_bwd_impl": (_I, [_I]),
+    "mf_set_dynamic_tiles": (_I, [_I]),
     "mf_tc_check_error": (_I, []),
     "mf_debug_umma_linear": (_I, [_P, _P, _P, _I, _I, _P]),
     "mf_debug_umma_dgrad": (_I, [_P, _P, _P, _I, _P]),
     "mf_debug_umma_wgrad": (_I, [_P, _P, _P, _I, _I, _P]),
     "mf_debug_profile": (_I, [_I, _P]),
+    "mf_debug_profile_all": (_I, [_P, _I]),
     "mf_debug_kernel_timer": (_I, [_I]),
     "mf_debug_kernel_ms": (_I, [_I, _P]),
     "mf_hashgrid_meta": (_I, [_I, _I, _I, _I, _D, C.POINTER(GridMeta)]),

@@ -88,13 +88,14 @@ template <class Src, class Epi, bool SDF_ONLY>
 __global__ void __launch_bounds__(2 * T3_GT, 1) field_fwd_tc3_kernel(FieldDev f, Src src, Epi epi, int64_t N,
                                                                      const unsigned int* __restrict__ n_dev,
                                                                      const uint8_t* __restrict__ img, int* __restrict__ err,
-                                                                     long long* __restrict__ prof) {
+                                                                     long long* __restrict__ prof, int* __restrict__ tile_ctr = nullptr) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint32_t tmem_ptr_s;
     // profiling stamps (mf_debug_profile): CTA 0, third tile; producers -> prof[40..], consumers -> prof[48..]
 #define T3_MARK(slot) do { if (prof && blockIdx.x == 0 && tid == 0 && k == 2) prof[slot] = clock64(); } while (0)
     if (n_dev) N = (int64_t)*n_dev;
     if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[29] = clock64();
+    if (prof && threadIdx.x == 0 && blockIdx.x < 256) prof[64 + 2 * blockIdx.x] = mf_globaltimer();
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(base + T3S_BAR);            // [0] mma, [1,2] full, [3,4] empty
     for (int i = threadIdx.x; i < IMG_BYTES / 16; i += blockDim.x)
@@ -117,24 +118,44 @@ __global__ void __launch_bounds__(2 * T3_GT, 1) field_fwd_tc3_kernel(FieldDev f,
     const float* fw = (const float*)(base + IMG_F32);
     const int64_t n_tiles = (N + TC_TP - 1) / TC_TP;
     bool ok = true;
+    // Tile queue.  The first two tiles of a CTA are static (blockIdx.x, blockIdx.x + gridDim.x); from the third on an elected
+    // producer thread draws the tile of iteration k + 2 from a global counter while it works on iteration k and leaves it in
+    // tq[(k + 2) & 3] (tile_ctr == NULL: static striding through the same queue).  SMs do not run this kernel at the same
+    // speed -- measured CTA lifetimes at C1 with static striding: 124 .. 163 us (scripts/prof_cta.py) -- so the fast ones take
+    // more tiles.  Which CTA evaluates a tile does not change any result.
+    volatile int* tq = reinterpret_cast<volatile int*>(base + T3S_BAR + 40);
+    if (threadIdx.x < 4) tq[threadIdx.x] = 0;              // (before the first rendezvous below; speculative reads see a valid tile)
 
     if (producer) {
         // =========================== producers: encode into the staging columns ===========================
         const float2* grid2 = reinterpret_cast<const float2*>(f.grid);
-        uint32_t k = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+        for (uint32_t k = 0;; ++k) {
             const int s = (int)(k & 1u);
             const uint32_t stg = lane_base + (uint32_t)(T3_STG + T3_STG_COLS * s);
             float* cpart = (float*)(base + T3S_CPART) + s * T3_CPART_ROWS * TC_LD;
-            const int64_t i = tile * TC_TP + p;
-            const bool valid = i < N;
             T3_MARK(40);
             if (prof && blockIdx.x == 0 && tid == 0 && k < 12) prof[16 + k] = clock64();      // per-tile start stamps
+            // The point is loaded BEFORE the wait below (its latency hides behind it), from a speculative read of the tile queue:
+            // the entry was written a whole tile period ago, but only the wait orders this thread after that write -- so the entry
+            // is read again afterwards and the point reloaded in the (never observed) case that the two reads differ.
+            const int64_t tile_e = k < 2 ? (int64_t)blockIdx.x + (int64_t)k * gridDim.x : (int64_t)tq[k & 3u];
             float x[3] = {0.f, 0.f, 0.f};
-            if (valid) src.point(i, f, x);
+            if (tile_e >= 0 && tile_e < n_tiles && tile_e * TC_TP + p < N) src.point(tile_e * TC_TP + p, f, x);
             // stage s is free once the layer-3 MMAs of the tile that used it two tiles ago have completed
             ok &= umma::mbar_wait(bars + 3 + s, ((k >> 1) & 1u) ^ 1u);
             umma::fence_after_sync();
+            const int64_t tile = k < 2 ? tile_e : (int64_t)tq[k & 3u];
+            if (tile >= n_tiles) break;
+            if (tid == 0) {                                // publish the tile of iteration k + 2 (see the tile queue note above)
+                const int64_t t2 = tile_ctr ? 2 * (int64_t)gridDim.x + atomicAdd(tile_ctr, 1) : tile + 2 * (int64_t)gridDim.x;
+                tq[(k + 2u) & 3u] = (int)(t2 < n_tiles ? t2 : n_tiles);
+            }
+            const int64_t i = tile * TC_TP + p;
+            const bool valid = i < N;
+            if (tile != tile_e) {
+                x[0] = x[1] = x[2] = 0.f;
+                if (valid) src.point(i, f, x);
+            }
             T3_MARK(41);
             // ---- frequency features: this thread owns slot groups 2h, 2h+1 ----
             float r[3] = {0.f, 0.f, 0.f};
@@ -204,9 +225,11 @@ __global__ void __launch_bounds__(2 * T3_GT, 1) field_fwd_tc3_kernel(FieldDev f,
         T3Cons c;
         c.img = base; c.fw = fw; c.part = (float*)(base + T3S_PART); c.out = (float*)(base + T3S_OUT); c.bar = bars;
         c.tmem = tmem; c.lane_base = lane_base; c.phase = 0; c.tid = tid; c.ok = true;
-        uint32_t k = 0;
         float v[32];
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+        for (uint32_t k = 0;; ++k) {
+            // (the queue entry of iteration k was written before the producers handed over tile k - 2, which this role has waited for)
+            const int64_t tile = k < 2 ? (int64_t)blockIdx.x + (int64_t)k * gridDim.x : (int64_t)tq[k & 3u];
+            if (tile >= n_tiles) break;
             const int s = (int)(k & 1u);
             const int stg = T3_STG + T3_STG_COLS * s;
             const float* cpart = (const float*)(base + T3S_CPART) + s * T3_CPART_ROWS * TC_LD;
@@ -361,5 +384,10 @@ __global__ void __launch_bounds__(2 * T3_GT, 1) field_fwd_tc3_kernel(FieldDev f,
     umma::fence_before_sync();
     __syncthreads();
     if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[28] = clock64();
+    if (prof && threadIdx.x == 0 && blockIdx.x < 256) prof[65 + 2 * blockIdx.x] = mf_globaltimer();
+    if (tile_ctr && threadIdx.x == 0 && atomicAdd(tile_ctr + 1, 1) == (int)gridDim.x - 1) {     // last CTA out re-arms the counter pair
+        tile_ctr[0] = 0; tile_ctr[1] = 0;
+        __threadfence();
+    }
     if ((threadIdx.x >> 5) == 0) umma::tmem_dealloc<512>(tmem);
 }

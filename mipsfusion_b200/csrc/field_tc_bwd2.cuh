@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
     using namespace b2;
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5;
+    if (prof && tid == 0 && blockIdx.x < 256) prof[576 + 2 * blockIdx.x] = mf_globaltimer();
     float* gpart = part + (size_t)blockIdx.x * MF_MLP_PARAMS;
     for (int i = tid; i < MF_MLP_PARAMS; i += B2_NT) gpart[i] = 0.f;
 
@@ -754,5 +755,6 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
     if (!c.ok && err) atomicExch(err, 1);
     umma::fence_before_sync();
     __syncthreads();
+    if (prof && tid == 0 && blockIdx.x < 256) prof[577 + 2 * blockIdx.x] = mf_globaltimer();
     if (warp == 0) umma::tmem_dealloc<512>(c.tmem);
 }

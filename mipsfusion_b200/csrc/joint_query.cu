@@ -4,7 +4,7 @@
 #include "field_launch.cuh"
 #include "field_tc_launch.cuh"
 
-constexpr int64_t JQ_CHUNK = 4 << 20;        // points per internal chunk (bounds the compacted index list)
+constexpr int64_t JQ_CHUNK = 16 << 20;        // points per internal chunk (bounds the compacted index list)
 
 struct PointSetDev {
     const double* pts; const double* ax; const double* ay; const double* az;
@@ -180,8 +180,11 @@ MF_API int mf_joint_query_accumulate(const mf_point_set* ps, const mf_submap* su
             MF_LAUNCH_CHECK();
             SrcJoint src{p, sub, list, g_begin + c_begin};
             EpiJoint epi{p, sub, list, g_begin + c_begin, c_begin, vis, M, m, max_dist, color, acc, mask_any};
-            if (color) rc = launch_field_fwd_auto<SrcJoint, EpiJoint, false>(d, src, epi, c_count, st, counter, true);
-            else rc = launch_field_fwd_auto<SrcJoint, EpiJoint, true>(d, src, epi, c_count, st, counter, true);
+            // launches with few tiles per CTA cannot fill the producer -> consumer pipeline: dual-pipeline kernel for those; at
+            // mesh resolution (512^3: ~30 tiles per CTA and chunk) the producer / consumer kernel is 12 % faster (0.165 vs 0.188 s)
+            const bool dual = c_count < (1 << 20);
+            if (color) rc = launch_field_fwd_auto<SrcJoint, EpiJoint, false>(d, src, epi, c_count, st, counter, dual);
+            else rc = launch_field_fwd_auto<SrcJoint, EpiJoint, true>(d, src, epi, c_count, st, counter, dual);
             if (rc) return rc;
         }
     }

@@ -57,6 +57,26 @@ MF_API int mf_set_bwd_impl(int impl) {
     return MF_OK;
 }
 
+static int* g_tile_ctr[64] = {nullptr};
+static unsigned g_tile_next[64] = {0};
+static int g_dynamic_tiles = 1;
+constexpr int TILE_CTR_RING = 256;
+int* mf_tile_counter() {
+    if (!g_dynamic_tiles) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!g_tile_ctr[dev]) {
+        if (cudaMalloc(&g_tile_ctr[dev], TILE_CTR_RING * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+        cudaMemset(g_tile_ctr[dev], 0, TILE_CTR_RING * 2 * sizeof(int));
+    }
+    return g_tile_ctr[dev] + 2 * (g_tile_next[dev]++ % TILE_CTR_RING);
+}
+// A/B switch: 1 (default) = tiles of the producer / consumer forward kernel are drawn from a global counter, 0 = static striding.
+MF_API int mf_set_dynamic_tiles(int on) {
+    g_dynamic_tiles = on ? 1 : 0;
+    return MF_OK;
+}
+
 static int* g_tc_err[64] = {nullptr};
 int* mf_tc_error_flag() {
     int dev = 0;
@@ -87,8 +107,8 @@ long long* mf_tc_profile_buffer() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     if (!g_prof[dev]) {
-        if (cudaMalloc(&g_prof[dev], 64 * sizeof(long long)) != cudaSuccess) return nullptr;
-        cudaMemset(g_prof[dev], 0, 64 * sizeof(long long));
+        if (cudaMalloc(&g_prof[dev], MF_PROF_SLOTS * sizeof(long long)) != cudaSuccess) return nullptr;
+        cudaMemset(g_prof[dev], 0, MF_PROF_SLOTS * sizeof(long long));
     }
     return g_prof[dev];
 }
@@ -102,6 +122,17 @@ MF_API int mf_debug_profile(int on, long long* out_host) {
         if (g_prof[dev]) MF_CUDA(cudaMemcpy(out_host, g_prof[dev], 64 * sizeof(long long), cudaMemcpyDeviceToHost));
         else memset(out_host, 0, 64 * sizeof(long long));
     }
+    return MF_OK;
+}
+
+// All MF_PROF_SLOTS stamps: [0, 64) as mf_debug_profile; [64 + 2 b, +1] = globaltimer (ns) at the start / end of CTA b of the last
+// profiled field_fwd_tc3_kernel, [576 + 2 b, +1] the same for field_bwd_tc2_kernel (b < 256).
+MF_API int mf_debug_profile_all(long long* out_host, int n) {
+    MF_CHECK_ARG(out_host && n >= 0 && n <= MF_PROF_SLOTS);
+    int dev = 0;
+    MF_CUDA(cudaGetDevice(&dev));
+    if (g_prof[dev]) MF_CUDA(cudaMemcpy(out_host, g_prof[dev], (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
+    else memset(out_host, 0, (size_t)n * sizeof(long long));
     return MF_OK;
 }
 

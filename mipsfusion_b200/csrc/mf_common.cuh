@@ -109,7 +109,13 @@ int mf_field_to_dev(const mf_field* f, FieldDev* d);   // validates (16 levels, 
 int mf_decoder_impl();                                 // 0: tcgen05 tensor cores (default), 1: fp32 CUDA cores
 int mf_bwd_impl();                                     // tensor-core backward: 0 role-split kernel (default), 1 single-role kernel
 int* mf_tc_error_flag();
-long long* mf_tc_profile_buffer();                     // device buffer of 64 clock stamps, or nullptr when profiling is off                               // device int, set by a kernel whose MMA wait timed out
+// {next tile, CTAs done} pair for one launch of a kernel with dynamic tile scheduling (zero on entry, re-armed by the last CTA of
+// the launch); drawn round-robin from a per-device ring, so launches in flight on different streams do not share a pair.
+// mf_set_dynamic_tiles(0) -> NULL (static striding, A/B).
+int* mf_tile_counter();
+constexpr int MF_PROF_SLOTS = 1024;
+long long* mf_tc_profile_buffer();
+__device__ __forceinline__ long long mf_globaltimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }                     // device buffer of 64 clock stamps, or nullptr when profiling is off                               // device int, set by a kernel whose MMA wait timed out
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -16,6 +16,9 @@ if mode == "ro":
     cfg, of = bench.build_model()
     model = H.cuda_model(cfg, H.state_of(of))
     print(bench.tracking_bench(model, cfg, dev, iters=iters))
+elif mode == "jq512":
+    r = bench.joint_query_bench(dev, res=512)
+    print({k: v for k, v in r.items() if not isinstance(v, dict)})
 elif mode == "jq":
     print(bench.joint_query_bench(dev, res=128))
 elif mode == "go":                       # fused gradient pose refinement: ray-gradient-only tensor-core backward
