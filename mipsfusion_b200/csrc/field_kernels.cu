@@ -582,7 +582,8 @@ static int launch_field_bwd(const FieldDev& d, const Src& src, const float* d_ra
                 field_bwd_tc3_kernel<Src><<<grid, b3::B3_NT, b3::SMEM, st>>>(d, src, d_raw, grad_grid, workspace, cta_scr, N, am, mf_tc_error_flag(), mf_tc_profile_buffer());
             } else {                                       // three roles (default)
                 int rc = set_smem(field_bwd_tc2_kernel<Src>, b2::SMEM); if (rc) return rc;
-                field_bwd_tc2_kernel<Src><<<grid, b2::B2_NT, b2::SMEM, st>>>(d, src, d_raw, grad_grid, workspace, cta_scr, N, am, mf_tc_error_flag(), mf_tc_profile_buffer());
+                field_bwd_tc2_kernel<Src><<<grid, b2::B2_NT, b2::SMEM, st>>>(d, src, d_raw, grad_grid, workspace, cta_scr, N, am, mf_tc_error_flag(), mf_tc_profile_buffer(),
+                                                                             mf_bwd_impl() == 2 ? 0 : 1);
             }
             mf_ktimer_end(1, st);
             MF_LAUNCH_CHECK();

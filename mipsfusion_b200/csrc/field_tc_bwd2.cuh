@@ -181,7 +181,7 @@ template <class Src>
 __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f, Src src, const float* __restrict__ d_raw,
                                                                   float* __restrict__ grad_grid, float* __restrict__ part,
                                                                   uint32_t* __restrict__ scratch, int64_t N_all, ActiveMap am,
-                                                                  int* __restrict__ err, long long* __restrict__ prof) {
+                                                                  int* __restrict__ err, long long* __restrict__ prof, int agg) {
     using namespace b2;
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -734,17 +734,20 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
             // use the unit just as much)
             if (prof && blockIdx.x == 0 && k == 1 && p == 0) prof[26] = clock64();
 #ifndef MF_EXP_NOSCATTER
-            if (valid) {
-                float dx[3];
+            {
+                // (slots behind the end of the list carry an all-zero gradient row: they join the runs with zeros and are skipped)
 #pragma unroll 1
                 for (int gq = 0; gq < 4; ++gq) {         // rolled over groups of 4 levels: three roles share the instruction cache
                     float dy8[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        dy8[j] = __uint_as_float(gq == 0 ? r[j] : (gq == 1 ? r[8 + j] : (gq == 2 ? r[16 + j] : r[24 + j])));
-#pragma unroll
-                    for (int ll = 0; ll < 4; ++ll)
-                        grid_level_bwd<false>(x, make_float2(dy8[2 * ll], dy8[2 * ll + 1]), nullptr, grad_grid, level_info(f, gq * 4 + ll), dx);
+                        dy8[j] = valid ? __uint_as_float(gq == 0 ? r[j] : (gq == 1 ? r[8 + j] : (gq == 2 ? r[16 + j] : r[24 + j]))) : 0.f;
+#pragma unroll 1
+                    for (int ll = 0; ll < 4; ++ll) {
+                        const float2 dy = ll == 0 ? make_float2(dy8[0], dy8[1]) : (ll == 1 ? make_float2(dy8[2], dy8[3]) : (ll == 2 ? make_float2(dy8[4], dy8[5]) : make_float2(dy8[6], dy8[7])));
+                        if (agg) grid_level_scatter_agg(x, dy, grad_grid, level_info(f, gq * 4 + ll), tid & 31);
+                        else if (valid) { float dx[3]; grid_level_bwd<false>(x, dy, nullptr, grad_grid, level_info(f, gq * 4 + ll), dx); }
+                    }
                 }
             }
 #endif

@@ -146,6 +146,55 @@ __device__ __forceinline__ void grid_level_bwd(const float x[3], float2 dy, cons
     }
 }
 
+// Warp-aggregated scatter of one level (all 32 lanes of the warp call it together; lane = point, consecutive lanes = consecutive
+// active points = mostly consecutive samples of one ray).  Consecutive samples share their cell on the coarse levels -- the samples
+// a loss term sees sit within the truncation distance of the surface, a few centimetres apart -- so lanes are grouped into runs of
+// equal cell (compare with the previous lane, one ballot), the eight corner contributions are summed along each run with a
+// segmented shuffle scan (as many doubling steps as the longest run needs; none when every run has length one), and only the
+// last lane of a run issues the reductions: the SM's reduction rate is per lane (1.29 cycles), a shuffle step is not.
+// Same values as grid_level_bwd up to the order of the float additions (the atomics already leave that order open).
+__device__ __forceinline__ void grid_level_scatter_agg(const float x[3], float2 dy, float* __restrict__ grad, const LevelInfo& li, int lane) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    uint32_t g[3]; float fr[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) pos_fract(x[d], li.scale, g[d], fr[d]);
+    const bool same = (__shfl_up_sync(FULL, g[0], 1) == g[0]) & (__shfl_up_sync(FULL, g[1], 1) == g[1]) & (__shfl_up_sync(FULL, g[2], 1) == g[2]);
+    const uint32_t heads = __ballot_sync(FULL, lane == 0 || !same);
+    const int off = lane - (31 - __clz((int)(heads & (FULL >> (31 - lane)))));       // distance to the head of this lane's run
+    const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+    uint32_t idx[8]; float w8[8];
+    grid_corners(x, li, idx, w8);
+    float vx[8], vy[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { vx[c] = w8[c] * dy.x; vy[c] = w8[c] * dy.y; }
+    if (heads != FULL) {                                   // (warp-uniform)
+#pragma unroll 1
+        for (int d = 1; d < 32; d <<= 1) {
+            if (!__any_sync(FULL, off >= d)) break;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float ax = __shfl_up_sync(FULL, vx[c], d), ay = __shfl_up_sync(FULL, vy[c], d);
+                if (off >= d) { vx[c] += ax; vy[c] += ay; }
+            }
+        }
+    }
+    if (tail) {
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {                   // x-pairs that are table neighbours leave as one 16-byte reduction (grid_level_bwd)
+            if (vx[c] == 0.f && vy[c] == 0.f && vx[c + 1] == 0.f && vy[c + 1] == 0.f) continue;
+            const uint32_t i0 = idx[c], i1 = idx[c + 1];
+            if ((i0 ^ i1) == 1u) {
+                const bool sw = (i0 & 1u) != 0u;
+                red_add_f4(grad + 2 * (size_t)(li.offset + (i0 & ~1u)), sw ? vx[c + 1] : vx[c], sw ? vy[c + 1] : vy[c], sw ? vx[c] : vx[c + 1],
+                           sw ? vy[c] : vy[c + 1]);
+            } else {
+                red_add_f2(grad + 2 * (size_t)(li.offset + i0), vx[c], vy[c]);
+                red_add_f2(grad + 2 * (size_t)(li.offset + i1), vx[c + 1], vy[c + 1]);
+            }
+        }
+    }
+}
+
 // Coordinate normalisation of JointEncoding.run_network (model/scene_rep.py:138-142) followed by
 // "/ norm_factor" (:119): fp64 arithmetic, one rounding to fp32 (the bound tensors are float64).
 __device__ __forceinline__ void normalize_point(const FieldDev& f, const float p[3], float x[3]) {

@@ -48,11 +48,12 @@ MF_API int mf_set_decoder_impl(int impl) {
 MF_API int mf_get_decoder_impl(void) { return g_decoder_impl; }
 
 // A/B switch of the tensor-core backward: 0 three-role kernel (field_tc_bwd2.cuh, default), 1 single-role kernel
-// (field_tc_bwd.cuh), 3 four-role kernel (field_tc_bwd3.cuh: correct, measured slower).
+// (field_tc_bwd.cuh), 2 three-role kernel without the warp-aggregated scatter, 3 four-role kernel (field_tc_bwd3.cuh: correct,
+// measured slower).
 static int g_bwd_impl = 0;
 int mf_bwd_impl() { return g_bwd_impl; }
 MF_API int mf_set_bwd_impl(int impl) {
-    MF_CHECK_ARG(impl == 0 || impl == 1 || impl == 3);
+    MF_CHECK_ARG(impl >= 0 && impl <= 3);
     g_bwd_impl = impl;
     return MF_OK;
 }

@@ -12,7 +12,7 @@ ro, rd, rgb, d, _ = bench.make_inputs(0)
 ro, rd, rgb, d = (t.cuda().contiguous() for t in (ro, rd, rgb, d))
 m = FusedMapper(model)
 L.call("mf_debug_kernel_timer", 1)
-for impl in (0, 1, 0):
+for impl in (0, 2, 0, 2, 1, 0):
     L.call("mf_set_bwd_impl", impl)
     for _ in range(3): m.step(ro, rd, rgb, d)
     ts = []

@@ -171,11 +171,18 @@ def test_training_loop_parity():
         loss = t["rgb_weight"] * ret["rgb_loss"] + t["sdf_weight"] * ret["sdf_loss"] + t["fs_weight"] * ret["fs_loss"]
         loss.backward(); opt_c.step(zero_grad=True)
         lo.append(float(loss_o)); lc.append(float(loss))
+    lo_a, lc_a = np.array(lo), np.array(lc)
+    dw = np.abs(model.decoder.pts_linear[0].weight.detach().cpu().numpy() - of.w["pts_linear.0.weight"].detach().numpy())
+    print("\n  loss curve max rel diff", float(np.max(np.abs(lc_a - lo_a) / np.abs(lo_a))), "first 5 steps", float(np.max(np.abs(lc_a[:5] - lo_a[:5]) / np.abs(lo_a[:5]))))
+    print("  weights after 30 steps: |diff| quantiles 50/99/100 %", np.quantile(dw, 0.5), np.quantile(dw, 0.99), dw.max())
+    # The first steps are a pure fp32-vs-tensor-core comparison: inside north_star's 1e-3 (measured 4.6e-4).  After that the
+    # comparison measures Adam, not the kernels: m / sqrt(v) turns the last digits of a near-zero gradient component into a
+    # +-lr step (lr = 1e-2 here), for ANY two fp32 implementations, and 30 such steps separate the two trajectories by a few
+    # 1e-3 on the loss (measured 3.8e-3) and by up to ~2 lr on single weights (measured: median 7e-4, 99 % 8e-3, max 2.2e-2).
+    np.testing.assert_allclose(lc_a[:5], lo_a[:5], rtol=1e-3)
     np.testing.assert_allclose(lc, lo, rtol=5e-3)
+    assert np.quantile(dw, 0.5) < 2e-3 and np.quantile(dw, 0.99) < 2e-2 and dw.max() < 5e-2, (np.quantile(dw, 0.5), np.quantile(dw, 0.99), dw.max())
     assert lc[-1] < lc[0]
-    # Adam normalises the gradient, so ulp-level differences on near-zero gradients become +-lr steps:
-    # after 30 steps only a loose bound on the weights is meaningful (the loss curve above is the real check)
-    assert H.rel_err(model.decoder.pts_linear[0].weight.detach().cpu(), of.w["pts_linear.0.weight"].detach()) < 0.1
 
 
 @pytest.mark.gpu
@@ -254,10 +261,12 @@ def test_backward_active_point_list_edge_cases(N, pattern, impl):
         assert float(gg.abs().max()) == 0.0 and (gp is None or float(gp.abs().max()) == 0.0)
         assert all(float(p.grad.abs().max()) == 0.0 for p in model.decoder.parameters())
         return
-    tol = 1e-4 if impl == 1 else 2e-3              # fp32 decoder / tcgen05 decoder (bf16 x 3): parameter gradients
-    assert H.rel_err(gg, of.grid.grad) < tol
-    for name, p in model.decoder.named_parameters():
-        assert H.rel_err(p.grad.cpu(), of.w[name].grad) < tol, name
+    tol = 1e-5 if impl == 1 else 1e-4              # fp32 decoder (measured <= 5e-7) / tcgen05 decoder, bf16 x 3 (measured <= 1.5e-5)
+    errs = {"grid": H.rel_err(gg, of.grid.grad)}
+    errs.update({name: H.rel_err(p.grad.cpu(), of.w[name].grad) for name, p in model.decoder.named_parameters()})
+    print(f"\n  N={N} {pattern} impl={impl}: max rel err {max(errs.values()):.2e} ({max(errs, key=errs.get)})")
+    for name, e in errs.items():
+        assert e < tol, (name, e)
     if want_dp:
         assert H.rel_err(gp, po.grad) < 1e-3
 
