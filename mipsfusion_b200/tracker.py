@@ -65,31 +65,80 @@ class FusedPoseRefiner:
             self._bufs[(R, S)] = b
         return b
 
-    def refine(self, c2w_init, rays_d_cam, target_rgb, target_d, n_iter, u=None, EMD_w=0.0):
+    def refine(self, c2w_init, rays_d_cam, target_rgb, target_d, n_iter, u=None, EMD_w=0.0, graph=None):
         """c2w_init (4,4); rays_d_cam (N,3) camera-frame directions, target_rgb (N,3), target_d (N,) or (N,1): device tensors of
         the pixels sampled once for the whole loop (:512-522).  u: optional (n_iter, N, S) stratified-jitter draws.
-        -> (c2w (4,4) device tensor: the best pose if ``use_best`` else the reference's `c2w_est`, state tensor).  No synchronisation."""
+        -> (c2w (4,4) device tensor: the best pose if ``use_best`` else the reference's `c2w_est`, state tensor).  No synchronisation.
+
+        graph (default: on when ``u`` is None): the whole loop -- n_iter x 15 launches -- is captured once per (N, S, n_iter,
+        weights buffers) as a CUDA graph on static input buffers and replayed; the loop is launch-bound (15 kernels of 5-120 us
+        per iteration against ~165 us of host time to issue them)."""
         model, dev = self.model, self.dev
         R = rays_d_cam.shape[0]
         cfg, lins = model._render_cfg(True, EMD_w, dev)
         S = cfg.n_samples_d + cfg.n_range_d
         b = self._buffers(R, S)
-        st = L.stream()
         field = model._field()
-        rays_d_cam, target_rgb = L.f32c(rays_d_cam, dev), L.f32c(target_rgb, dev)
-        target_d = L.f32c(target_d, dev).reshape(R)
+        if "in_dirs" not in b:
+            f32 = dict(device=dev, dtype=torch.float32)
+            b["in_dirs"], b["in_rgb"], b["in_d"] = torch.empty(R, 3, **f32), torch.empty(R, 3, **f32), torch.empty(R, **f32)
+            b["ws"] = torch.empty(int(L.lib().mf_field_bwd_workspace_size(R * S, 1)), **f32)
+        b["in_dirs"].copy_(rays_d_cam.reshape(R, 3), non_blocking=True)
+        b["in_rgb"].copy_(target_rgb.reshape(R, 3), non_blocking=True)
+        b["in_d"].copy_(target_d.reshape(R), non_blocking=True)
         c2w0 = torch.as_tensor(c2w_init).detach().to("cpu", torch.float32)
         init = torch.zeros(32)
         init[0:4] = matrix_to_quaternion(c2w0[:3, :3]); init[4:7] = c2w0[:3, 3]; init[22] = -1.0
         b["state"].copy_(init.to(dev, non_blocking=True))
-        ws = _Workspace.get(dev, field_points=R * S, want_ray_grads=True)
         if self.backward == "fp32":                    # the fp32 kernel always forms the parameter gradients: give it a sink
             fb = model._field(impl=1)
             if "sink" not in b:
                 b["sink"] = (torch.zeros_like(model.embed_fn.params.data), torch.zeros(L.MF_MLP_PARAMS, device=dev, dtype=torch.float32))
+        else:
+            fb = field
+        n_iter = int(n_iter)
+        use_graph = (u is None) if graph is None else bool(graph)
+        if use_graph and u is None and n_iter > 0 and not self.__dict__.get("_graph_off", False):
+            key = (R, S, n_iter, float(EMD_w), self.backward, field.grid, field.mlp_prep, fb.mlp_prep, int(cfg.perturb))
+            g = b.get("graph")
+            if g is None or g[0] != key:
+                try:
+                    self._loop(b, cfg, lins, field, fb, R, S, 1, None)          # eager warm-up: lazy allocations, function attributes
+                    b["state"].copy_(init.to(dev, non_blocking=True))
+                    torch.cuda.current_stream(dev).synchronize()
+                    cg = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(cg):
+                        self._loop(b, cfg, lins, field, fb, R, S, n_iter, None)
+                    g = b["graph"] = (key, cg, (field._keepalive, fb._keepalive))
+                    b["state"].copy_(init.to(dev, non_blocking=True))            # (the capture itself does not run anything)
+                except Exception as e:                                            # capture not possible here: stay on the eager loop
+                    self.__dict__["_graph_off"] = True
+                    self.__dict__["_graph_error"] = repr(e)
+                    g = None
+                    b.pop("graph", None)
+                    b["state"].copy_(init.to(dev, non_blocking=True))
+            if g is not None:
+                g[1].replay()
+                self.launches += 15 * n_iter
+                return (b["best"], b["state"]) if self.use_best else (b["c2w"][0], b["state"])
+        self._loop(b, cfg, lins, field, fb, R, S, n_iter, u)
+        if self.use_best and n_iter > 0:
+            return b["best"], b["state"]
+        # tracking.best = False: the reference hands back `c2w_est`, the matrix it formed at the START of the last executed
+        # iteration (mipsfusion.py:544,562-563) -- the last Adam step is never evaluated.  b["c2w"] holds exactly that matrix.
+        if n_iter <= 0:
+            L.call("mf_pose_to_c2w", L.ptr(b["state"]), L.ptr(b["c2w"]), L.stream())
+        return b["c2w"][0], b["state"]
+
+    def _loop(self, b, cfg, lins, field, fb, R, S, n_iter, u):
+        """n_iter iterations of the 15-launch sequence on the static buffers of ``b`` (current stream: also the capture stream)."""
+        dev = self.dev
+        st = L.stream()
+        rays_d_cam, target_rgb, target_d, ws = b["in_dirs"], b["in_rgb"], b["in_d"], b["ws"]
+        if self.backward == "fp32":
             gg, gm, feat_b = b["sink"][0], b["sink"][1], None
         else:
-            fb, gg, gm, feat_b = field, None, None, b["feat"]
+            gg, gm, feat_b = None, None, b["feat"]
         for it in range(int(n_iter)):
             L.call("mf_pose_to_c2w", L.ptr(b["state"]), L.ptr(b["c2w"]), st)
             L.call("mf_gen_rays", L.ptr(rays_d_cam), L.ptr(b["c2w"]), None, L.ptr(b["o"]), L.ptr(b["d"]), R, 1, st)
@@ -110,10 +159,3 @@ class FusedPoseRefiner:
             L.call("mf_pose_refine_update", L.ptr(b["state"]), L.ptr(b["c2w"]), L.ptr(b["d_c2w"]), L.ptr(b["losses"]), L.ptr(self.loss_w),
                    self.lr_rot, self.lr_trans, self.wait_iters, L.ptr(b["best"]), st)
             self.launches += 15
-        if self.use_best and n_iter > 0:
-            return b["best"], b["state"]
-        # tracking.best = False: the reference hands back `c2w_est`, the matrix it formed at the START of the last executed
-        # iteration (mipsfusion.py:544,562-563) -- the last Adam step is never evaluated.  b["c2w"] holds exactly that matrix.
-        if n_iter <= 0:
-            L.call("mf_pose_to_c2w", L.ptr(b["state"]), L.ptr(b["c2w"]), st)
-        return b["c2w"][0], b["state"]
