@@ -715,7 +715,9 @@ def joint_query_bench(dev, res=512, n_submaps=16, group=None, shard="points", pr
     axes = [np.linspace(lo[k], hi[k], res) for k in range(3)]
     jq = mf.JointSubmapQuery(models, poses, amin, amax, cents)
     kw = {} if group is None else dict(group=group, shard=shard)
-    jq.query(axes=[a_[:64] for a_ in axes], **kw)                # warm-up
+    jq.query(axes=[a_[:64] for a_ in axes], **kw)                # warm-up: kernels, ...
+    out = jq.query(axes=axes, **kw)                              # ... and the 1.3 GB of result / work buffers (cudaMalloc is not the query)
+    del out
     torch.cuda.synchronize()
     if group is not None:
         import torch.distributed as dist

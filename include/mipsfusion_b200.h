@@ -219,6 +219,17 @@ int mf_adam_step_multi(int n_tensors, float* const* p_host, float* const* g_host
                        float* const* v_host, const int64_t* n_host, double lr, double beta1, double beta2, double eps,
                        double weight_decay, int step, int zero_grad, void* stream);
 
+/* ---- N3: submap containment tests of the Manager (Manager.py:159-244; helper_functions/geometry_helper.py:193-203) ----
+ * n points -- either `pts` (n,3) as given, or the surface points t + (R dirs_cam[i]) * depth[i] of a frame with camera-to-world
+ * pose `pose_c2w` (16 floats, row major, device), formed in the reference's fp32 operation order -- against k axis-aligned boxes
+ * (xyz_min / xyz_max (k,3)), strict comparisons as pts_in_bbox.  cross != 0: every direction is paired with every depth (n * n
+ * points, direction-major) -- what the broadcast of Manager.py:174 ((P,1,3) * (P,1)) actually evaluates in
+ * find_highest_containing_ratio; compute_containing_ratio (:214) pairs them one to one (cross = 0).
+ * mask (points,k) uint8 and / or counts (2k+1) int64: [0,k) points inside box j, [k,2k) points inside box j whose depth is > 0,
+ * [2k] points with depth > 0 (pts: all valid). */
+int mf_containment(const float* dirs_cam, const float* depth, const float* pose_c2w, const float* pts, const float* xyz_min,
+                   const float* xyz_max, int k, int64_t n, int cross, uint8_t* mask, int64_t* counts, void* stream);
+
 /* ---- a11: pixel samplers (helper_functions/sampling_helper.py:7-68), int64 outputs ---- */
 int mf_sample_pixels_uniform(int img_h, int img_w, int num_h, int num_w, int64_t* rows, int64_t* cols, void* stream);
 /* top-`num` of keys*mask(depth>0 [and not on the lattice]) by (value desc, index asc); keys (H*W) >= 0.

@@ -17,3 +17,4 @@ from .render_full import render_full_img  # noqa: F401
 from .tracker import FusedPoseRefiner  # noqa: F401
 from .submap_parallel import SubmapParallel  # noqa: F401
 from . import sampling_helper  # noqa: F401
+from .manager import SubmapContainment, pts_in_bbox  # noqa: F401

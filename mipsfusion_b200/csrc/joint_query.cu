@@ -199,3 +199,71 @@ MF_API int mf_joint_query_finalize(const float* acc, const uint8_t* mask_any, in
     MF_LAUNCH_CHECK();
     return MF_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// N3: containment of a frame's surface points in the submaps' axis-aligned boxes
+// (Manager.find_highest_containing_ratio / compute_containing_ratio, Manager.py:159-244; pts_in_bbox, geometry_helper.py:193-203).
+// One thread per sampled pixel: world point = t + (R d_cam) * depth with the reference's fp32 operation order (three products
+// summed left to right, then multiply, then add: torch.sum(d[..., None, :] * R, -1), rays_o + rays_d * depth), strict
+// comparisons against every box, integer counts (deterministic).
+// counts: [0, k) points inside box j; [k, 2k) points inside box j with depth > 0; [2k] points with depth > 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) containment_kernel(const float* __restrict__ dirs_cam, const float* __restrict__ depth,
+                                                          const float* __restrict__ pose, const float* __restrict__ pts_in,
+                                                          const float* __restrict__ xyz_min, const float* __restrict__ xyz_max,
+                                                          int k, int64_t n, int64_t n_depth, uint8_t* __restrict__ mask,
+                                                          unsigned long long* __restrict__ counts) {
+    // n_depth > 0: every direction is paired with every depth (n = n_dirs * n_depth points; see mf_containment)
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = i < n;
+    float p[3] = {0.f, 0.f, 0.f};
+    bool valid = false;
+    if (on) {
+        if (pts_in) {
+            p[0] = pts_in[i * 3]; p[1] = pts_in[i * 3 + 1]; p[2] = pts_in[i * 3 + 2];
+            valid = true;
+        } else {
+            const int64_t id = n_depth > 0 ? i / n_depth : i, ip = n_depth > 0 ? i % n_depth : i;
+            const float dx = dirs_cam[id * 3], dy = dirs_cam[id * 3 + 1], dz = dirs_cam[id * 3 + 2], dep = depth[ip];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float dw = __fadd_rn(__fadd_rn(__fmul_rn(dx, pose[j * 4]), __fmul_rn(dy, pose[j * 4 + 1])), __fmul_rn(dz, pose[j * 4 + 2]));
+                p[j] = __fadd_rn(pose[j * 4 + 3], __fmul_rn(dw, dep));
+            }
+            valid = dep > 0.f;
+        }
+    }
+    const int lane = threadIdx.x & 31;
+    for (int j = 0; j < k; ++j) {
+        bool in = on;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) in = in && (p[d] > xyz_min[j * 3 + d]) && (p[d] < xyz_max[j * 3 + d]);
+        if (mask && on) mask[i * k + j] = in ? 1 : 0;
+        if (counts) {
+            const unsigned b_all = __ballot_sync(0xffffffffu, in), b_val = __ballot_sync(0xffffffffu, in && valid);
+            if (lane == 0) {
+                if (b_all) atomicAdd(&counts[j], (unsigned long long)__popc(b_all));
+                if (b_val) atomicAdd(&counts[k + j], (unsigned long long)__popc(b_val));
+            }
+        }
+    }
+    if (counts) {
+        const unsigned b = __ballot_sync(0xffffffffu, on && valid);
+        if (lane == 0 && b) atomicAdd(&counts[2 * k], (unsigned long long)__popc(b));
+    }
+}
+
+MF_API int mf_containment(const float* dirs_cam, const float* depth, const float* pose_c2w, const float* pts, const float* xyz_min,
+                          const float* xyz_max, int k, int64_t n, int cross, uint8_t* mask, int64_t* counts, void* stream) {
+    MF_CHECK_ARG(n >= 0 && k >= 1 && xyz_min && xyz_max && (mask || counts) && !(cross && pts));
+    const int64_t n_depth = cross ? n : 0;
+    if (cross) n = n * n;
+    MF_CHECK_ARG(pts || (dirs_cam && depth && pose_c2w));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (counts) MF_CUDA(cudaMemsetAsync(counts, 0, (size_t)(2 * k + 1) * sizeof(int64_t), st));
+    if (n == 0) return MF_OK;
+    containment_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dirs_cam, depth, pose_c2w, pts, xyz_min, xyz_max, k, n, n_depth, mask,
+                                                                    reinterpret_cast<unsigned long long*>(counts));
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}

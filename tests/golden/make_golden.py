@@ -308,13 +308,55 @@ def gen_keyframes():
     np.savez_compressed(os.path.join(OUT, "keyframes.npz"), **out)
 
 
+def gen_manager():
+    """The containment tests of the reference's OWN Manager (Manager.py:159-244), called unbound on a stand-in `self` that carries
+    only the attributes the two methods read (dataset.H / W, kfSet.localMLP_info, min_cr_localMLP_len): lattice scores,
+    the chosen submap and containing ratios on a synthetic frame with a few zero-depth pixels."""
+    from Manager import Manager
+    from mipsfusion_b200 import synth
+    g = torch.Generator().manual_seed(11)
+    dirs = synth.camera_rays()[::2, ::2].contiguous()            # (230, 310, 3): a half-resolution frame keeps the fixture small
+    H, W = dirs.shape[0], dirs.shape[1]
+    c2w = synth.trajectory(6)[2]
+    depth = synth.render_frame(c2w, dirs)["depth"].clone()
+    depth[torch.rand(H, W, generator=g) < 0.03] = 0.0            # missing depth
+    k = 6
+    centers = torch.tensor([1.0, 3.5, 1.0]) + 1.5 * (torch.rand(k, 3, generator=g) - 0.5)
+    lens = 1.0 + 3.0 * torch.rand(k, 3, generator=g)
+    info = torch.cat([torch.zeros(k, 1), centers, lens], -1)     # kfSet.localMLP_info rows: [flag, center 3, length 3]
+    stub = types.SimpleNamespace(dataset=types.SimpleNamespace(H=H, W=W), kfSet=types.SimpleNamespace(localMLP_info=info),
+                                 min_cr_localMLP_len=torch.tensor([2.0, 2.0, 2.0]))
+    ids = torch.arange(k)
+    out = dict(depth=depth.numpy(), c2w=c2w.numpy(),                # (dirs: synth.camera_rays()[::2, ::2], regenerated by the tests)
+               centers=centers.numpy(), lens=lens.numpy(),
+               min_len=stub.min_cr_localMLP_len.numpy())
+    out["top_id"] = np.int64(Manager.find_highest_containing_ratio(stub, depth, dirs, c2w, ids))
+    # the scores the method ranks (its Step 2, recomputed with the reference's own helpers)
+    from helper_functions.geometry_helper import pts_in_bbox as ref_pib
+    ih, iw = ref_samp.sample_pixels_uniformly(H, W, 15, 20)
+    td, dc = depth[ih, iw], dirs[ih, iw]
+    pts = (c2w[:3, -1].repeat(300, 1)[..., None, :] + torch.sum(dc[..., None, :] * c2w[None, :3, :3], -1)[..., None, :] * td[..., :, None]).reshape(-1, 3)
+    # NB the reference's expression broadcasts (P,1,3) * (P,1) to (P,P,3): every ray direction is paired with every depth
+    # (Manager.py:174) -- 90,000 points for the 15 x 20 lattice; that is the behaviour the scores below come from
+    out["scores"] = torch.count_nonzero(ref_pib(pts, centers - 0.5 * lens, centers + 0.5 * lens), dim=0).numpy()
+    sub = torch.randperm(pts.shape[0], generator=g)[:2000]
+    out["pts_sub"] = pts[sub].numpy()
+    out["mask_sub"] = ref_pib(pts[sub], centers - 0.5 * lens, centers + 0.5 * lens).numpy()
+    out["ratios"] = np.array([float(Manager.compute_containing_ratio(stub, depth, dirs, c2w, torch.tensor(j))) for j in range(k)], dtype=np.float64)
+    out["ratios_small"] = np.array([float(Manager.compute_containing_ratio(stub, depth, dirs, c2w, torch.tensor(j), rays_h=30, rays_w=40)) for j in range(k)], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "manager.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "keyframes":
         gen_keyframes(); sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "manager":
+        gen_manager(); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "overlap":
         gen_overlap(); sys.exit(0)
     gen_overlap()
     gen_keyframes()
+    gen_manager()
     gen_lattice(); gen_sampling(); gen_losses(); gen_decoder()
     cfg, model = gen_scene()
     gen_ro(cfg, model)
