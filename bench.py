@@ -417,14 +417,17 @@ def tracking_bench(model, cfg, dev, iters=5, group=None):
     target_d = sub["depth"].reshape(-1).to(dev); rays_d = dirs[rows, cols].contiguous().to(dev)
     rot, trans = c2w[:3, :3].contiguous().to(dev), c2w[:3, 3].contiguous().to(dev)
     search = torch.full((6,), 0.02, device=dev)
+    # the loop body of RandomOptimizer.optimize (score + swarm update, in place on copies of the pose state) on a fixed lattice
+    rot_s, trans_s, search_s = rot.clone(), trans.clone(), search.clone()
+    def body():
+        ro.iterate(model, rot_s, trans_s, search_s, target_d, rays_d)
     for _ in range(2):
-        ro.score(model, rot, trans, search, target_d, rays_d)
+        body()
     a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     a.record()
     for _ in range(iters):
-        fit, ms, p7 = ro.score(model, rot, trans, search, target_d, rays_d)
-        ro.update(fit, ms, p7, rot.clone(), trans.clone(), search.clone())
+        body()
     b.record(); torch.cuda.synchronize()
     ms_it = _max_over_ranks(a.elapsed_time(b) / iters, dev, group)
     model.train()

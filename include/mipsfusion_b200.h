@@ -304,6 +304,11 @@ int mf_ro_score(const float* particles6, const float* search_size, const float* 
 int mf_ro_update(const float* fitness, const float* mean_sdf, const float* pst7, int C, double rescale,
                  float* rot_cur, float* trans_cur, float* search_size, uint8_t* better_mask, int32_t* info,
                  void* stream);
+/* The same update reading the result of an all-gather in place: `gathered` = per-rank blocks of 9 * per floats
+ * [fitness (per) | mean_sdf (per) | pst7 (per x 7)], candidate c in block c / per at row c % per (multi-GPU RandomOptimizer:
+ * every rank's mf_ro_score writes one such block, one all-gather, no pack / unpack copies). */
+int mf_ro_update_gathered(const float* gathered, int C, int per, double rescale, float* rot_cur, float* trans_cur,
+                          float* search_size, uint8_t* better_mask, int32_t* info, void* stream);
 
 /* ---- a14: joint multi-submap query + blend (model/Mesher.py:464-528,606-663; vis/math_helper.py:58-96) ----
  * Query points are either explicit (pts (G,3) fp64 world coordinates, as trimesh vertices) or a regular

@@ -255,13 +255,14 @@ __global__ void __launch_bounds__(256) containment_kernel(const float* __restric
 
 MF_API int mf_containment(const float* dirs_cam, const float* depth, const float* pose_c2w, const float* pts, const float* xyz_min,
                           const float* xyz_max, int k, int64_t n, int cross, uint8_t* mask, int64_t* counts, void* stream) {
-    MF_CHECK_ARG(n >= 0 && k >= 1 && xyz_min && xyz_max && (mask || counts) && !(cross && pts));
-    const int64_t n_depth = cross ? n : 0;
-    if (cross) n = n * n;
-    MF_CHECK_ARG(pts || (dirs_cam && depth && pose_c2w));
+    MF_CHECK_ARG(n >= 0 && k >= 1);
     cudaStream_t st = (cudaStream_t)stream;
     if (counts) MF_CUDA(cudaMemsetAsync(counts, 0, (size_t)(2 * k + 1) * sizeof(int64_t), st));
-    if (n == 0) return MF_OK;
+    if (n == 0) return MF_OK;                          // (an empty point set has no buffers to check)
+    MF_CHECK_ARG(xyz_min && xyz_max && (mask || counts) && !(cross && pts));
+    MF_CHECK_ARG(pts || (dirs_cam && depth && pose_c2w));
+    const int64_t n_depth = cross ? n : 0;
+    if (cross) n = n * n;
     containment_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dirs_cam, depth, pose_c2w, pts, xyz_min, xyz_max, k, n, n_depth, mask,
                                                                     reinterpret_cast<unsigned long long*>(counts));
     MF_LAUNCH_CHECK();

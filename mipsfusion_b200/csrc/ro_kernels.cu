@@ -105,8 +105,11 @@ __global__ void __launch_bounds__(1024) ro_reduce_kernel(const float* __restrict
 }
 
 // Swarm update (single CTA): RandomOptimizer.py:202-224
+// per > 0: the three inputs are the gathered per-rank blocks [fitness (per) | mean_sdf (per) | pst7 (per x 7)] (9 per floats per
+// rank, `fitness` points at the first block): candidate c lives in block c / per at row c % per -- the layout an all-gather of
+// each rank's contiguous result buffer produces, read in place (no pack / unpack copies).
 __global__ void __launch_bounds__(1024) ro_update_kernel(const float* __restrict__ fitness, const float* __restrict__ mean_sdf,
-                                                         const float* __restrict__ pst7, int C, float rescale,
+                                                         const float* __restrict__ pst7, int C, int per, float rescale,
                                                          float* __restrict__ rot_cur, float* __restrict__ trans_cur,
                                                          float* __restrict__ search_size, uint8_t* __restrict__ better_mask,
                                                          int32_t* __restrict__ info) {
@@ -117,7 +120,11 @@ __global__ void __launch_bounds__(1024) ro_update_kernel(const float* __restrict
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};       // sum w, sum w*mean_sdf, sum w*pst7[0..6]
     int cnt = 0, arg = 0x7fffffff; float fmin_ = INFINITY;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float f = fitness[c];
+        const float* blk = per > 0 ? fitness + (size_t)(c / per) * 9 * per : nullptr;
+        const int row = per > 0 ? c % per : c;
+        const float* msdf_ = per > 0 ? blk + per : mean_sdf;
+        const float* p7_ = per > 0 ? blk + 2 * per : pst7;
+        const float f = per > 0 ? blk[row] : fitness[c];
         const bool better = f < f0;
         if (better_mask) better_mask[c] = better ? 1 : 0;
         if (f < fmin_) { fmin_ = f; arg = c; }
@@ -125,9 +132,9 @@ __global__ void __launch_bounds__(1024) ro_update_kernel(const float* __restrict
             const float w = f0 - f;
             cnt += 1;
             acc[0] += (double)w;
-            acc[1] += (double)(w * mean_sdf[c]);
+            acc[1] += (double)(w * msdf_[row]);
 #pragma unroll
-            for (int k = 0; k < 7; ++k) acc[2 + k] += (double)(pst7[(size_t)c * 7 + k] * w);
+            for (int k = 0; k < 7; ++k) acc[2 + k] += (double)(p7_[(size_t)row * 7 + k] * w);
         }
     }
     const int w_ = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -172,7 +179,7 @@ __global__ void __launch_bounds__(1024) ro_update_kernel(const float* __restrict
         for (int k = 0; k < 3; ++k) trans_cur[k] += mt[4 + k];
         mt6[0] = q[1]; mt6[1] = q[2]; mt6[2] = q[3]; mt6[3] = mt[4]; mt6[4] = mt[5]; mt6[5] = mt[6];
     } else {
-        mean_s = mean_sdf[0];
+        mean_s = per > 0 ? fitness[per] : mean_sdf[0];
         for (int k = 0; k < 6; ++k) mt6[k] = 0.f;                      // no_rel_trans[1:]
     }
     float s[6], n2 = 0.f;
@@ -209,7 +216,16 @@ MF_API int mf_ro_score(const float* particles6, const float* search_size, const 
 MF_API int mf_ro_update(const float* fitness, const float* mean_sdf, const float* pst7, int C, double rescale, float* rot_cur,
                         float* trans_cur, float* search_size, uint8_t* better_mask, int32_t* info, void* stream) {
     MF_CHECK_ARG(C > 0 && fitness && mean_sdf && pst7 && rot_cur && trans_cur && search_size);
-    ro_update_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(fitness, mean_sdf, pst7, C, (float)rescale, rot_cur, trans_cur,
+    ro_update_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(fitness, mean_sdf, pst7, C, 0, (float)rescale, rot_cur, trans_cur,
+                                                           search_size, better_mask, info);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}
+
+MF_API int mf_ro_update_gathered(const float* gathered, int C, int per, double rescale, float* rot_cur, float* trans_cur,
+                                 float* search_size, uint8_t* better_mask, int32_t* info, void* stream) {
+    MF_CHECK_ARG(C > 0 && per > 0 && gathered && rot_cur && trans_cur && search_size);
+    ro_update_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(gathered, nullptr, nullptr, C, per, (float)rescale, rot_cur, trans_cur,
                                                            search_size, better_mask, info);
     MF_LAUNCH_CHECK();
     return MF_OK;

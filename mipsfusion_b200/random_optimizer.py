@@ -3,7 +3,8 @@
 (mf_ro_score / mf_ro_update) with no host synchronisation inside the iteration loop.
 
 Candidates shard naturally across GPUs: pass ``group`` (a torch.distributed process group) and every
-rank scores C/G candidates, followed by one small all-gather of (fitness, mean_sdf, pst7)."""
+rank scores C/G candidates, followed by one small all-gather of (fitness, mean_sdf, pst7) that the update kernel reads in
+place (``iterate``)."""
 import ctypes as C
 
 import numpy as np
@@ -90,6 +91,55 @@ class RandomOptimizer:
                    L.ptr(rot_cur), L.ptr(trans_cur), L.ptr(search_size), L.ptr(better), L.ptr(info), L.stream())
         return better, info
 
+    # ---- one iteration without intermediate tensors ---------------------------------------------------------------------
+    def _iter_buffers(self, P):
+        Cn = self.pre_sampled_particle.shape[0]
+        b, n, ws, rk = self._shard()
+        per = (Cn + ws - 1) // ws
+        buf = self.__dict__.get("_ibuf")
+        if buf is None or buf["key"] != (Cn, P, ws, rk):
+            dev = self.device
+            f32 = dict(device=dev, dtype=torch.float32)
+            buf = dict(key=(Cn, P, ws, rk), local=torch.zeros(9 * per, **f32), scratch=torch.empty(max(n, 1) * (P + 12), **f32),
+                       gathered=torch.empty(ws * 9 * per, **f32) if ws > 1 else None)
+            self.__dict__["_ibuf"] = buf
+        return buf, b, n, ws, per
+
+    def iterate(self, model, rot_cur, trans_cur, search_size, target_d, rays_d_cam, better=None, info=None):
+        """One loop body (RandomOptimizer.py:192-224): score this rank's candidates and apply the swarm update, in place on
+        ``rot_cur`` / ``trans_cur`` / ``search_size``.  The three per-candidate results of a rank are one contiguous block
+        [fitness | mean_sdf | pst7] on persistent buffers; with a process group the blocks are all-gathered once (9 floats per
+        candidate) and the update kernel reads the gathered blocks in place -- 4 launches + 1 collective per iteration, no
+        allocation, no pack / unpack copies.  better (C) uint8 / info (4) int32: optional outputs.  -> (blocks, per)."""
+        dev = self.device
+        Cn, P = self.pre_sampled_particle.shape[0], target_d.shape[0]
+        buf, b, n, ws, per = self._iter_buffers(P)
+        loc = buf["local"]
+        field = model._field()
+        with torch.cuda.device(dev):
+            st = L.stream()
+            L.call("mf_ro_score", L.ptr(self.pre_sampled_particle), L.ptr(search_size), L.ptr(rot_cur), L.ptr(trans_cur),
+                   L.ptr(rays_d_cam), L.ptr(target_d), C.byref(field), float(self.trunc_value), float(self.sdf_weight),
+                   int(b), int(n), int(P), loc.data_ptr(), loc.data_ptr() + 4 * per, loc.data_ptr() + 8 * per, L.ptr(buf["scratch"]), st)
+            blocks = loc
+            if ws > 1:
+                import torch.distributed as dist
+                blocks = buf["gathered"]
+                dist.all_gather_into_tensor(blocks, loc, group=self.group)
+            L.call("mf_ro_update_gathered", L.ptr(blocks), int(Cn), int(per), float(self.scaling_coefficient2), L.ptr(rot_cur),
+                   L.ptr(trans_cur), L.ptr(search_size), L.ptr(better), L.ptr(info), st)
+        return blocks, per
+
+    def _lattice(self, off):
+        """Pixel lattice shifted by ``off`` (RandomOptimizer.py:186-190) and its camera-frame directions (cached: they do not
+        depend on the frame)."""
+        cache = self.__dict__.setdefault("_lat", {})
+        e = cache.get(off)
+        if e is None:
+            ih, iw = self.row_indices + off, self.col_indices + off
+            e = cache[off] = (ih, iw, self.rays_dir[ih, iw, :].contiguous())
+        return e
+
     @torch.no_grad()
     def optimize(self, model, depth_img, initial_pose, last_frame_pose, n_iter=10):
         """reference RandomOptimizer.py:165-227; returns the tracked pose as a CPU (4,4) tensor."""
@@ -101,15 +151,15 @@ class RandomOptimizer:
         trans_cur = init[:3, 3].contiguous()
         search = torch.full((6,), float(self.scaling_coefficient1), device=dev, dtype=torch.float32)
         depth = L.f32c(torch.as_tensor(depth_img), dev)            # one H2D copy of the depth image
-        infos, fits, betters = [], [], []
+        Cn = self.pre_sampled_particle.shape[0]
+        infos = torch.empty(n_iter, 4, device=dev, dtype=torch.int32)
+        betters = torch.empty(n_iter, Cn, device=dev, dtype=torch.uint8)
+        fits = []
         for i in range(n_iter):
-            off = i % 5
-            ih, iw = self.row_indices + off, self.col_indices + off
+            ih, iw, rays_d_cam = self._lattice(i % 5)
             target_d = depth[ih, iw].contiguous()
-            rays_d_cam = self.rays_dir[ih, iw, :].contiguous()
-            fit, msdf, pst7 = self.score(model, rot_cur, trans_cur, search, target_d, rays_d_cam)
-            better, info = self.update(fit, msdf, pst7, rot_cur, trans_cur, search)
-            infos.append(info); fits.append(fit); betters.append(better)
-        self.last_info = torch.stack(infos)        # device tensors; reading them is the caller's sync point
-        self.last_fitness, self.last_better = fits, betters
+            blocks, per = self.iterate(model, rot_cur, trans_cur, search, target_d, rays_d_cam, better=betters[i], info=infos[i])
+            fits.append(blocks.view(-1, 9 * per)[:, :per].reshape(-1)[:Cn].clone() if per < Cn else blocks[:Cn].clone())   # diagnostics
+        self.last_info = infos                      # device tensors; reading them is the caller's sync point
+        self.last_fitness, self.last_better = fits, list(betters)
         return pose_compose(rot_cur.cpu(), trans_cur.cpu())
