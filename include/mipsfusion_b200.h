@@ -309,6 +309,14 @@ int mf_ro_update(const float* fitness, const float* mean_sdf, const float* pst7,
  * every rank's mf_ro_score writes one such block, one all-gather, no pack / unpack copies). */
 int mf_ro_update_gathered(const float* gathered, int C, int per, double rescale, float* rot_cur, float* trans_cur,
                           float* search_size, uint8_t* better_mask, int32_t* info, void* stream);
+/* Exchange + update in ONE kernel over NVLink peer memory (no collective call): peer_bases[r] = rank r's mapping of a
+ * symmetric float arena holding, at float offset off_gathered, 2 x world x 9 x per floats (double-buffered gathered blocks) and,
+ * at off_flags, `world` 32-bit sequence flags (zero-initialised).  The kernel stores `local_block` (this rank's 9 x per floats)
+ * into every rank's gathered buffer, publishes `seq` (1, 2, 3, ... in lockstep on all ranks) in every rank's flags, waits for
+ * all ranks' blocks and runs mf_ro_update on them.  A peer that never arrives sets the error flag (mf_tc_check_error). */
+int mf_ro_update_peer(const float* local_block, const uint64_t* peer_bases, int world, int rank, int64_t off_gathered,
+                      int64_t off_flags, unsigned int seq, int C, int per, double rescale, float* rot_cur, float* trans_cur,
+                      float* search_size, uint8_t* better_mask, int32_t* info, void* stream);
 
 /* ---- a14: joint multi-submap query + blend (model/Mesher.py:464-528,606-663; vis/math_helper.py:58-96) ----
  * Query points are either explicit (pts (G,3) fp64 world coordinates, as trimesh vertices) or a regular

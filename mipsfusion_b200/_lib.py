@@ -105,6 +105,7 @@ PROTOTYPES = {
     "mf_ro_score": (_I, [_P, _P, _P, _P, _P, _P, C.POINTER(Field), _D, _D, _I, _I, _I, _P, _P, _P, _P, _P]),
     "mf_ro_update": (_I, [_P, _P, _P, _I, _D, _P, _P, _P, _P, _P, _P]),
     "mf_ro_update_gathered": (_I, [_P, _I, _I, _D, _P, _P, _P, _P, _P, _P]),
+    "mf_ro_update_peer": (_I, [_P, _P, _I, _I, _L, _L, C.c_uint, _I, _I, _D, _P, _P, _P, _P, _P, _P]),
     "mf_joint_query_scratch_size": (_L, [_L]),
     "mf_joint_query_maxdist": (_I, [C.POINTER(PointSet), C.POINTER(Submap), _I, _L, _L, _P, _P]),
     "mf_joint_query_accumulate": (_I, [C.POINTER(PointSet), C.POINTER(Submap), _I, _I, _I, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P]),

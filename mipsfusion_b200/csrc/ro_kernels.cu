@@ -108,15 +108,15 @@ __global__ void __launch_bounds__(1024) ro_reduce_kernel(const float* __restrict
 // per > 0: the three inputs are the gathered per-rank blocks [fitness (per) | mean_sdf (per) | pst7 (per x 7)] (9 per floats per
 // rank, `fitness` points at the first block): candidate c lives in block c / per at row c % per -- the layout an all-gather of
 // each rank's contiguous result buffer produces, read in place (no pack / unpack copies).
-__global__ void __launch_bounds__(1024) ro_update_kernel(const float* __restrict__ fitness, const float* __restrict__ mean_sdf,
-                                                         const float* __restrict__ pst7, int C, int per, float rescale,
-                                                         float* __restrict__ rot_cur, float* __restrict__ trans_cur,
-                                                         float* __restrict__ search_size, uint8_t* __restrict__ better_mask,
-                                                         int32_t* __restrict__ info) {
+__device__ __forceinline__ void ro_update_body(const float* __restrict__ fitness, const float* __restrict__ mean_sdf,
+                                               const float* __restrict__ pst7, int C, int per, float rescale,
+                                               float* __restrict__ rot_cur, float* __restrict__ trans_cur,
+                                               float* __restrict__ search_size, uint8_t* __restrict__ better_mask,
+                                               int32_t* __restrict__ info) {
     __shared__ double red[32][9];
     __shared__ int red_cnt[32], red_arg[32];
     __shared__ float red_min[32];
-    const float f0 = fitness[0];
+    const float f0 = per > 0 ? __ldcg(fitness) : fitness[0];
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};       // sum w, sum w*mean_sdf, sum w*pst7[0..6]
     int cnt = 0, arg = 0x7fffffff; float fmin_ = INFINITY;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(1024) ro_update_kernel(const float* __restrict
         const int row = per > 0 ? c % per : c;
         const float* msdf_ = per > 0 ? blk + per : mean_sdf;
         const float* p7_ = per > 0 ? blk + 2 * per : pst7;
-        const float f = per > 0 ? blk[row] : fitness[c];
+        const float f = per > 0 ? __ldcg(blk + row) : fitness[c];
         const bool better = f < f0;
         if (better_mask) better_mask[c] = better ? 1 : 0;
         if (f < fmin_) { fmin_ = f; arg = c; }
@@ -132,9 +132,9 @@ __global__ void __launch_bounds__(1024) ro_update_kernel(const float* __restrict
             const float w = f0 - f;
             cnt += 1;
             acc[0] += (double)w;
-            acc[1] += (double)(w * msdf_[row]);
+            acc[1] += (double)(w * (per > 0 ? __ldcg(msdf_ + row) : msdf_[row]));
 #pragma unroll
-            for (int k = 0; k < 7; ++k) acc[2 + k] += (double)(p7_[(size_t)row * 7 + k] * w);
+            for (int k = 0; k < 7; ++k) acc[2 + k] += (double)((per > 0 ? __ldcg(p7_ + (size_t)row * 7 + k) : p7_[(size_t)row * 7 + k]) * w);
         }
     }
     const int w_ = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(1024) ro_update_kernel(const float* __restrict
         for (int k = 0; k < 3; ++k) trans_cur[k] += mt[4 + k];
         mt6[0] = q[1]; mt6[1] = q[2]; mt6[2] = q[3]; mt6[3] = mt[4]; mt6[4] = mt[5]; mt6[5] = mt[6];
     } else {
-        mean_s = per > 0 ? fitness[per] : mean_sdf[0];
+        mean_s = per > 0 ? __ldcg(fitness + per) : mean_sdf[0];
         for (int k = 0; k < 6; ++k) mt6[k] = 0.f;                      // no_rel_trans[1:]
     }
     float s[6], n2 = 0.f;
@@ -190,6 +190,51 @@ __global__ void __launch_bounds__(1024) ro_update_kernel(const float* __restrict
         search_size[k] = success ? ss : ss * 2.0f;
     }
     if (info) { info[0] = count; info[1] = success ? 1 : 0; info[2] = amin; info[3] = 0; }
+}
+
+__global__ void __launch_bounds__(1024) ro_update_kernel(const float* __restrict__ fitness, const float* __restrict__ mean_sdf,
+                                                         const float* __restrict__ pst7, int C, int per, float rescale,
+                                                         float* __restrict__ rot_cur, float* __restrict__ trans_cur,
+                                                         float* __restrict__ search_size, uint8_t* __restrict__ better_mask,
+                                                         int32_t* __restrict__ info) {
+    ro_update_body(fitness, mean_sdf, pst7, C, per, rescale, rot_cur, trans_cur, search_size, better_mask, info);
+}
+
+// Multi-GPU iteration without a collective library call: every rank's update kernel first stores its own result block
+// (9 per floats) into the gathered buffer of EVERY rank over NVLink peer memory, publishes a sequence number in every rank's
+// flag array (release, system scope), waits until all ranks' numbers have arrived in its own flag array (acquire), and then
+// runs the swarm update on its local copy of the gathered blocks -- exchange and update are one single-CTA kernel.
+// The gathered buffer is double-buffered by the parity of the sequence number: a rank can publish iteration i + 1 only after
+// its own update of iteration i, and nobody can start i + 2 before everybody published i + 1.
+constexpr int RO_MAX_PEERS = 16;
+struct RoPeers { float* gathered[RO_MAX_PEERS]; unsigned int* flags[RO_MAX_PEERS]; };
+
+__global__ void __launch_bounds__(1024) ro_update_peer_kernel(const float* __restrict__ local_block, RoPeers peers, int rank, int world,
+                                                              unsigned int seq, int C, int per, float rescale,
+                                                              float* __restrict__ rot_cur, float* __restrict__ trans_cur,
+                                                              float* __restrict__ search_size, uint8_t* __restrict__ better_mask,
+                                                              int32_t* __restrict__ info, int* __restrict__ err) {
+    const int n = 9 * per;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = local_block[i];
+        for (int r = 0; r < world; ++r) __stcg(peers.gathered[r] + (size_t)rank * n + i, v);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        const int r = threadIdx.x;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.flags[r] + rank), "r"(seq) : "memory");
+        // wait for rank r's block (bounded: a missing peer must not hang the GPU)
+        const unsigned int* mine = peers.flags[rank] + r;
+        unsigned int got = 0;
+        for (long long it = 0; it < (1ll << 28); ++it) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine) : "memory");
+            if ((int)(got - seq) >= 0) break;
+        }
+        if ((int)(got - seq) < 0 && err) atomicExch(err, 1);
+    }
+    __syncthreads();
+    ro_update_body(peers.gathered[rank], nullptr, nullptr, C, per, rescale, rot_cur, trans_cur, search_size, better_mask, info);
 }
 
 MF_API int mf_ro_score(const float* particles6, const float* search_size, const float* rot_cur, const float* trans_cur,
@@ -218,6 +263,25 @@ MF_API int mf_ro_update(const float* fitness, const float* mean_sdf, const float
     MF_CHECK_ARG(C > 0 && fitness && mean_sdf && pst7 && rot_cur && trans_cur && search_size);
     ro_update_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(fitness, mean_sdf, pst7, C, 0, (float)rescale, rot_cur, trans_cur,
                                                            search_size, better_mask, info);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}
+
+MF_API int mf_ro_update_peer(const float* local_block, const uint64_t* peer_bases, int world, int rank, int64_t off_gathered,
+                             int64_t off_flags, unsigned int seq, int C, int per, double rescale, float* rot_cur, float* trans_cur,
+                             float* search_size, uint8_t* better_mask, int32_t* info, void* stream) {
+    MF_CHECK_ARG(local_block && peer_bases && world >= 1 && world <= RO_MAX_PEERS && rank >= 0 && rank < world);
+    MF_CHECK_ARG(C > 0 && per > 0 && (int64_t)per * world >= C && rot_cur && trans_cur && search_size && off_gathered >= 0 && off_flags >= 0);
+    RoPeers peers;
+    const int64_t n = 9 * (int64_t)per * world;
+    for (int r = 0; r < world; ++r) {
+        MF_CHECK_ARG(peer_bases[r]);
+        float* base = reinterpret_cast<float*>(peer_bases[r]);
+        peers.gathered[r] = base + off_gathered + (seq & 1u) * n;           // double-buffered by the parity of the sequence number
+        peers.flags[r] = reinterpret_cast<unsigned int*>(base + off_flags);
+    }
+    ro_update_peer_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(local_block, peers, rank, world, seq, C, per, (float)rescale, rot_cur,
+                                                                trans_cur, search_size, better_mask, info, mf_tc_error_flag());
     MF_LAUNCH_CHECK();
     return MF_OK;
 }

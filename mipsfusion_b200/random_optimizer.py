@@ -24,7 +24,7 @@ def pose_compose(rot_mat, trans_vec):
 
 
 class RandomOptimizer:
-    def __init__(self, cfg, mipsfusion, particles=None, group=None):
+    def __init__(self, cfg, mipsfusion, particles=None, group=None, peer_memory="auto"):
         self.cfg = cfg
         self.slam = mipsfusion
         self.dataset = self.slam.dataset
@@ -48,6 +48,7 @@ class RandomOptimizer:
                                                                      device=self.device)
         self.fx, self.fy, self.cx, self.cy = self.dataset.fx, self.dataset.fy, self.dataset.cx, self.dataset.cy
         self.group = group
+        self.peer_memory = peer_memory     # multi-GPU exchange: True (require NVLink peer memory), False (NCCL all-gather), "auto"
         self.last_info = None          # per-iteration (count, success, argmin) of the last optimize() call
         self.last_fitness = None
 
@@ -103,6 +104,23 @@ class RandomOptimizer:
             buf = dict(key=(Cn, P, ws, rk), local=torch.zeros(9 * per, **f32), scratch=torch.empty(max(n, 1) * (P + 12), **f32),
                        gathered=torch.empty(ws * 9 * per, **f32) if ws > 1 else None)
             self.__dict__["_ibuf"] = buf
+        if ws > 1 and self.peer_memory and "_arena" not in self.__dict__:
+            # symmetric (peer-mapped) arena for the exchange inside the update kernel; every rank reaches this point in its first
+            # iteration (the rendezvous is collective).  Not available (no NVLink peer access, gloo tests): NCCL all-gather.
+            arena = None
+            try:
+                arena = D.PeerArena({"gath": 2 * ws * 9 * per, "flags": ws}, self.device, self.group, use_multicast=False)
+                torch.cuda.current_stream(self.device).synchronize()
+                arena.barrier()
+                torch.cuda.current_stream(self.device).synchronize()
+            except Exception as e:
+                if self.peer_memory is True:
+                    raise
+                self.__dict__["_arena_error"] = repr(e)
+                arena = None
+            self.__dict__["_arena"] = arena
+            self.__dict__["_arena_per"] = per
+            self.__dict__["_seq"] = 0
         return buf, b, n, ws, per
 
     def iterate(self, model, rot_cur, trans_cur, search_size, target_d, rays_d_cam, better=None, info=None):
@@ -122,6 +140,18 @@ class RandomOptimizer:
                    L.ptr(rays_d_cam), L.ptr(target_d), C.byref(field), float(self.trunc_value), float(self.sdf_weight),
                    int(b), int(n), int(P), loc.data_ptr(), loc.data_ptr() + 4 * per, loc.data_ptr() + 8 * per, L.ptr(buf["scratch"]), st)
             blocks = loc
+            arena = self.__dict__.get("_arena") if ws > 1 else None
+            if arena is not None and self.__dict__["_arena_per"] == per:
+                # exchange + update in one kernel over NVLink peer memory (mf_ro_update_peer): no collective call
+                self.__dict__["_seq"] += 1
+                seq = self.__dict__["_seq"]
+                bases = (C.c_uint64 * ws)(*arena.peer_bases)
+                L.call("mf_ro_update_peer", L.ptr(loc), bases, int(ws), int(arena.rank), int(arena.offsets["gath"]), int(arena.offsets["flags"]),
+                       int(seq & 0xFFFFFFFF), int(Cn), int(per), float(self.scaling_coefficient2), L.ptr(rot_cur), L.ptr(trans_cur),
+                       L.ptr(search_size), L.ptr(better), L.ptr(info), st)
+                n = ws * 9 * per
+                blocks = arena.view("gath")[(seq & 1) * n:(seq & 1) * n + n]
+                return blocks, per
             if ws > 1:
                 import torch.distributed as dist
                 blocks = buf["gathered"]

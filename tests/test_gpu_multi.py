@@ -166,3 +166,56 @@ def test_submap_parallel_on_two_gpus(tmp_path):
         assert H.rel_err(r["ovl_grad"], ref) < 5e-2                  # (one sample on a cell boundary, see test_overlap.py)
     r1 = np.load(out + ".1.npz")
     assert bool(r1["handoff_exact"]) and float(r1["handoff_query_err"]) < 1e-4
+
+
+def _ro_worker(rank, world, port, out):
+    import types
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import mipsfusion_b200 as mf
+    from mipsfusion_b200 import synth
+    cfg = H.make_config(14)
+    cfg["tracking"] = {"RO": {"particle_size": 300, "initial_scaling_factor": 0.02, "rescaling_factor": 0.5, "n_rows": 12, "n_cols": 16},
+                       "ignore_edge_W": 20, "ignore_edge_H": 20}
+    of = H.oracle_field(cfg, grid_scale=0.3, seed=4)
+    model = H.cuda_model(cfg, H.state_of(of), train=False)
+    dirs = synth.camera_rays()
+    c2w = synth.trajectory(4)[1]
+    depth = synth.render_frame(c2w, dirs)["depth"]
+    ds = types.SimpleNamespace(H=460, W=620, fx=320.0, fy=320.0, cx=309.5, cy=229.5, rays_d=dirs)
+    g = torch.Generator().manual_seed(1)
+    particles = torch.randn(300, 6, generator=g).clamp(-2, 2); particles[0] = 0
+    slam = types.SimpleNamespace(dataset=ds, device=str(dev))
+    start = c2w.clone(); start[:3, 3] += torch.tensor([0.01, -0.01, 0.005])
+    res = {}
+    for name, kw in (("single", dict(group=None)), ("nccl", dict(group=dist.group.WORLD, peer_memory=False)),
+                     ("peer", dict(group=dist.group.WORLD, peer_memory=True))):
+        ro = mf.RandomOptimizer(cfg, slam, particles=particles.clone(), **kw)
+        poses = [ro.optimize(model, depth, start.clone(), start.clone(), n_iter=7).numpy().copy() for _ in range(2)]   # 14 exchanges: both buffer parities
+        torch.cuda.synchronize()
+        assert (ro.__dict__.get("_arena") is not None) == (name == "peer")
+        res[name] = (np.stack(poses), ro.last_info.cpu().numpy().copy())
+    from mipsfusion_b200 import _lib as L
+    assert L.lib().mf_tc_check_error() == 0
+    np.savez(out + f".{rank}.npz", **{f"{k}_pose": v[0] for k, v in res.items()}, **{f"{k}_info": v[1] for k, v in res.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_random_optimizer_sharded_routes_equal_single_gpu(tmp_path):
+    """RandomOptimizer with the 300 candidates sharded over two GPUs -- NCCL all-gather + update, and the one-kernel exchange +
+    update over NVLink peer memory -- against the single-GPU loop: per-candidate fitness is reduced in a fixed order and the
+    update kernel sums the candidates in a fixed order, so the tracked poses and the per-iteration decisions (better count,
+    success, argmin) must be bit-identical on every rank."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "ro")
+    mp.spawn(_ro_worker, args=(2, 29667, out), nprocs=2, join=True)
+    for rank in range(2):
+        r = np.load(out + f".{rank}.npz")
+        for name in ("nccl", "peer"):
+            np.testing.assert_array_equal(r[f"{name}_pose"], r["single_pose"])
+            np.testing.assert_array_equal(r[f"{name}_info"], r["single_info"])
