@@ -28,7 +28,7 @@ constexpr int T3S_CPART = ((IMG_BYTES + 127) / 128) * 128;
 constexpr int T3S_PART = T3S_CPART + 2 * T3_CPART_ROWS * TC_LD * 4;
 constexpr int T3S_OUT = T3S_PART + T3_PART_ROWS * TC_LD * 4;
 constexpr int T3S_BAR = T3S_OUT + MF_RAW_DIM * TC_LD * 4;
-constexpr size_t SMEM_TC3 = T3S_BAR + 64 + 1024;
+constexpr size_t SMEM_TC3 = T3S_BAR + 64 + 1024;                 // bars [0,5) | tile queue at +40 | image barrier [7] at +56
 static_assert(SMEM_TC3 <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ void t3_cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(T3_GT) : "memory"); }
@@ -98,26 +98,34 @@ __global__ void __launch_bounds__(2 * T3_GT, 1) field_fwd_tc3_kernel(FieldDev f,
     if (prof && threadIdx.x == 0 && blockIdx.x < 256) prof[64 + 2 * blockIdx.x] = mf_globaltimer();
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(base + T3S_BAR);            // [0] mma, [1,2] full, [3,4] empty
-    for (int i = threadIdx.x; i < IMG_BYTES / 16; i += blockDim.x)
-        reinterpret_cast<uint4*>(base)[i] = __ldg(reinterpret_cast<const uint4*>(img) + i);
-    umma::fence_proxy_async();
     if ((threadIdx.x >> 5) == 0) umma::tmem_alloc<512>(&tmem_ptr_s);
     if (threadIdx.x == 0) {
         umma::mbar_init(bars + 0, 1);
         umma::mbar_init(bars + 1, T3_GT); umma::mbar_init(bars + 2, T3_GT);
         umma::mbar_init(bars + 3, 1); umma::mbar_init(bars + 4, 1);
+        umma::mbar_init(bars + 7, 1);
         umma::fence_barrier_init();
+        // the weight image (166 KB) comes in through the bulk-copy engine while the CTA sets up (a copy loop over all threads
+        // took ~20 dependent L2 round trips per thread)
+        constexpr uint32_t CHUNK = 32768;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bars + 7)), "r"((uint32_t)IMG_BYTES) : "memory");
+        for (uint32_t off = 0; off < (uint32_t)IMG_BYTES; off += CHUNK) {
+            const uint32_t nb = (uint32_t)IMG_BYTES - off < CHUNK ? (uint32_t)IMG_BYTES - off : CHUNK;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(umma::smem_u32(base + off)), "l"(img + off), "r"(nb), "r"(umma::smem_u32(bars + 7)) : "memory");
+        }
     }
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
+    bool img_ok = umma::mbar_wait(bars + 7, 0);            // the image has landed (visible to this thread and to the tensor core)
     const uint32_t tmem = tmem_ptr_s;
     const bool producer = threadIdx.x < T3_GT;
     const int tid = threadIdx.x & (T3_GT - 1), p = tid & 127, h = tid >> 7;
     const uint32_t lane_base = tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16);
     const float* fw = (const float*)(base + IMG_F32);
     const int64_t n_tiles = (N + TC_TP - 1) / TC_TP;
-    bool ok = true;
+    bool ok = img_ok;
     // Tile queue.  The first two tiles of a CTA are static (blockIdx.x, blockIdx.x + gridDim.x); from the third on an elected
     // producer thread draws the tile of iteration k + 2 from a global counter while it works on iteration k and leaves it in
     // tq[(k + 2) & 3] (tile_ctr == NULL: static striding through the same queue).  SMs do not run this kernel at the same
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(2 * T3_GT, 1) field_fwd_tc3_kernel(FieldDev f,
         // =========================== consumers: decoder on the staged tile ===========================
         T3Cons c;
         c.img = base; c.fw = fw; c.part = (float*)(base + T3S_PART); c.out = (float*)(base + T3S_OUT); c.bar = bars;
-        c.tmem = tmem; c.lane_base = lane_base; c.phase = 0; c.tid = tid; c.ok = true;
+        c.tmem = tmem; c.lane_base = lane_base; c.phase = 0; c.tid = tid; c.ok = ok;
         float v[32];
         for (uint32_t k = 0;; ++k) {
             // (the queue entry of iteration k was written before the producers handed over tile k - 2, which this role has waited for)
