@@ -69,7 +69,7 @@ constexpr int SCR_H1 = 0, SCR_H3 = 128, SCR_RGB = 256, SCR_U = 320, SCR_WORDS = 
 constexpr int64_t SCR_CTA_WORDS = (int64_t)SCR_WORDS * TC_TP;
 constexpr int REGS_CHAIN = 160, REGS_WGRAD = 88, REGS_SCATTER = 104;       // 256 x 160 + 128 x 88 + 128 x 104 = 65,536
 // ---- mbarriers ----
-enum { B_MMA = 0, B_DG3, B_DCONS, B_DWFREE, B_DWRDY, B_W1, B_FREE0, B_ISS0 = B_FREE0 + 4, B_COUNT = B_ISS0 + 4 };   // B_FREE0 + q: MMAs of staged quarter q done
+enum { B_MMA = 0, B_DG3, B_DCONS, B_DWFREE, B_DWRDY, B_W1, B_IMG, B_FREE0, B_ISS0 = B_FREE0 + 4, B_COUNT = B_ISS0 + 4 };   // B_FREE0 + q: MMAs of staged quarter q done
 constexpr int N_X3 = 112;                              // wgrad-3 X width: 64 sdf_emb + 32 grid + ones column + padding to 16
 
 __device__ __forceinline__ void chain_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CHAIN_NT) : "memory"); }
@@ -193,24 +193,29 @@ __global__ void __launch_bounds__(b2::B2_NT, 1) field_bwd_tc2_kernel(FieldDev f,
     c.base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     c.fw = (const float*)(c.base + S_F32); c.part = (float*)(c.base + S_PART); c.bars = (uint64_t*)(c.base + S_BAR);
     uint32_t* tmem_ptr = (uint32_t*)(c.base + S_BAR + 8 * B_COUNT);
-    for (int i = tid; i < (IMG_F32 - IMG_W2_HI) / 16; i += B2_NT)
-        reinterpret_cast<uint4*>(c.base + S_W)[i] = __ldg(reinterpret_cast<const uint4*>(f.tc_img + IMG_W2_HI) + i);
-    for (int i = tid; i < F_COUNT * 4 / 16; i += B2_NT)
-        reinterpret_cast<uint4*>(c.base + S_F32)[i] = __ldg(reinterpret_cast<const uint4*>(f.tc_img + IMG_F32) + i);
-    umma::fence_proxy_async();
     if (warp == 0) umma::tmem_alloc<512>(tmem_ptr);
     if (tid == 0) {
         umma::mbar_init(c.bars + B_MMA, 1); umma::mbar_init(c.bars + B_DG3, 1); umma::mbar_init(c.bars + B_DCONS, SC_NT);
         umma::mbar_init(c.bars + B_DWFREE, WG_NT); umma::mbar_init(c.bars + B_DWRDY, 4); umma::mbar_init(c.bars + B_W1, 1);
+        umma::mbar_init(c.bars + B_IMG, 1);
         for (int q = 0; q < 4; ++q) { umma::mbar_init(c.bars + B_FREE0 + q, 1); umma::mbar_init(c.bars + B_ISS0 + q, 1); }
         umma::fence_barrier_init();
+        // resident weights (W2 | W3 images, fp32 section) through the bulk-copy engine while the CTA zero-fills its partials
+        constexpr uint32_t W_BYTES = IMG_F32 - IMG_W2_HI, F_BYTES = F_COUNT * 4, CHUNK = 32768;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(c.bars + B_IMG)), "r"(W_BYTES + F_BYTES) : "memory");
+        for (uint32_t off = 0; off < W_BYTES; off += CHUNK)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(umma::smem_u32(c.base + S_W + off)), "l"(f.tc_img + IMG_W2_HI + off), "r"(W_BYTES - off < CHUNK ? W_BYTES - off : CHUNK),
+                           "r"(umma::smem_u32(c.bars + B_IMG)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(umma::smem_u32(c.base + S_F32)), "l"(f.tc_img + IMG_F32), "r"(F_BYTES), "r"(umma::smem_u32(c.bars + B_IMG)) : "memory");
     }
     umma::fence_before_sync();
     __syncthreads();                                   // also orders the gpart zero-fill before WGRAD's reductions
     umma::fence_after_sync();
     c.tmem = *tmem_ptr;
     c.lane_base = c.tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    c.ok = true;
+    c.ok = umma::mbar_wait(c.bars + B_IMG, 0);         // the weights have landed
 
     const int64_t N = am.n(N_all);                     // active points only (ascending point indices in am.idx)
     const int64_t n_tiles = (N + TC_TP - 1) / TC_TP;
