@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_scene.py tests/test_gpu_tensorcore.py tests/test_gpu_baseline_shapes.py -x -q 2>&1 | tail -3
-timeout 300 python scripts/prof_bwd2.py 2>&1 | head -7
+timeout 600 python -m pytest tests/test_gpu_tensorcore.py -x -q -s 2>&1 | grep -v "^$" | grep -i "passed\|failed\|error\|grid  \|assert" | tail -12
+timeout 300 python scripts/prof_bwd2.py 2>&1 | head -30
