@@ -87,6 +87,9 @@ int mf_get_decoder_impl(void);
 int mf_set_bwd_impl(int impl);
 /* A/B switch of the forward kernel's tile scheduling: 1 = dynamic (global tile counter, default), 0 = static striding. */
 int mf_set_dynamic_tiles(int on);
+/* Number of SMs the forward kernel leaves free (default 0).  The data-parallel mapper sets 1 so that its count all-reduce, issued
+ * on the collective library's stream, overlaps the forward instead of waiting for an SM. */
+int mf_set_sm_reserve(int n);
 int mf_tc_check_error(void);
 /* Diagnostics: out (128,128) = x (128,K) w (128,K)^T through one tcgen05 layer; K % 16 == 0, K <= 128;
  * passes = 1 (bf16) or 3 (bf16x3 split). */

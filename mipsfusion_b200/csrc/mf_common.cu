@@ -27,6 +27,16 @@ int mf_sm_count_cached() {
     return cached[dev];
 }
 
+// SMs the producer / consumer forward kernel leaves free (its persistent CTAs fill an SM completely): lets a small collective
+// kernel issued on another stream -- the data-parallel mapper's 16-byte count all-reduce -- run beside it instead of behind it.
+static int g_sm_reserve = 0;
+int mf_sm_reserve() { return g_sm_reserve; }
+MF_API int mf_set_sm_reserve(int n) {
+    MF_CHECK_ARG(n >= 0 && n < 32);
+    g_sm_reserve = n;
+    return MF_OK;
+}
+
 MF_API int mf_device_sm_count(void) {
     int dev = 0, n = 0;
     MF_CUDA(cudaGetDevice(&dev));

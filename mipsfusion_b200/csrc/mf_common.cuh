@@ -113,6 +113,7 @@ int* mf_tc_error_flag();
 // the launch); drawn round-robin from a per-device ring, so launches in flight on different streams do not share a pair.
 // mf_set_dynamic_tiles(0) -> NULL (static striding, A/B).
 int* mf_tile_counter();
+int mf_sm_reserve();
 constexpr int MF_PROF_SLOTS = 1024;
 long long* mf_tc_profile_buffer();
 __device__ __forceinline__ long long mf_globaltimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }                     // device buffer of 64 clock stamps, or nullptr when profiling is off                               // device int, set by a kernel whose MMA wait timed out

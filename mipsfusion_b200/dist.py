@@ -44,6 +44,15 @@ def allreduce_sum_(t, group):
     return t
 
 
+def allreduce_sum_async_(t, group):
+    """Starts the all-reduce on the collective library's own stream (ordered after the work already queued on the current
+    stream); the caller queues independent kernels and then calls ``.wait()`` on the returned handle (None for a world of 1)."""
+    import torch.distributed as dist
+    if world(group)[0] > 1:
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True)
+    return None
+
+
 def allreduce_max_(t, group):
     import torch.distributed as dist
     if world(group)[0] > 1:

@@ -55,6 +55,8 @@ class FusedMapper:
                 import warnings
                 warnings.warn("FusedMapper: peer memory unavailable (%s); using NCCL all-reduce" % (e,))
                 self.arena = None
+        if self.world > 1 and self.dev.type == "cuda":
+            L.call("mf_set_sm_reserve", 1)                           # room for the count all-reduce beside the forward (step())
         self.step_count = 0
         self.pose_grad_impl = "tc"       # "tc": tensor-core backward (pose gradients 2.4e-4 vs the oracle), "fp32": CUDA cores (5e-7)
         self._bufs = {}
@@ -141,10 +143,14 @@ class FusedMapper:
         e0 = ev()
         L.call("mf_sample_z", L.ptr(target_d), L.ptr(u), L.ptr(lins[0]), L.ptr(lins[1]), L.ptr(lins[2]), C.byref(cfg),
                L.ptr(b["z"]), L.ptr(b["counts"]), R, st)
-        D.allreduce_sum_(b["counts"], self.group)                    # batch-global mask counts (utils.py:43-47)
+        # batch-global mask counts (utils.py:43-47): only the loss kernels need them, so the 16-byte all-reduce runs on the
+        # collective library's stream BESIDE the field forward (which leaves one SM free for it, mf_set_sm_reserve)
+        work = D.allreduce_sum_async_(b["counts"], self.group)
         e1 = ev()
         L.call("mf_field_query_rays", L.ptr(rays_o), L.ptr(rays_d), L.ptr(b["z"]), C.byref(field), L.ptr(b["raw"]), L.ptr(b["feat"]),
                R, S, st)
+        if work is not None:
+            work.wait()
         e2 = ev()
         L.call("mf_render_loss_fwd", L.ptr(b["raw"]), L.ptr(b["z"]), L.ptr(target_rgb), L.ptr(target_d), L.ptr(b["counts"]),
                C.byref(cfg), L.ptr(b["rgb"]), L.ptr(b["depth"]), None, None, None, L.ptr(b["losses"]), L.ptr(b["scratch"]), R, S, st)
