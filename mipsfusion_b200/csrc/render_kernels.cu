@@ -221,9 +221,12 @@ __global__ void __launch_bounds__(1024) loss_finalize_kernel(const float* __rest
                                                              RenderCfgDev c, float* __restrict__ losses, int64_t R, int S) {
     __shared__ double red[32][8];
     double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int64_t r = threadIdx.x; r < R; r += 1024)
-#pragma unroll
-        for (int k = 0; k < 7; ++k) s[k] += (double)scratch[r * 8 + k];
+    const float4* rows = reinterpret_cast<const float4*>(scratch);            // 8 floats per ray: two 16-byte loads
+    for (int64_t r = threadIdx.x; r < R; r += 1024) {
+        const float4 a = rows[2 * r], b = rows[2 * r + 1];
+        s[0] += (double)a.x; s[1] += (double)a.y; s[2] += (double)a.z; s[3] += (double)a.w;
+        s[4] += (double)b.x; s[5] += (double)b.y; s[6] += (double)b.z;
+    }
 #pragma unroll
     for (int k = 0; k < 7; ++k) s[k] = warp_sum_d(s[k]);
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -231,10 +234,11 @@ __global__ void __launch_bounds__(1024) loss_finalize_kernel(const float* __rest
 #pragma unroll
         for (int k = 0; k < 7; ++k) red[w][k] = s[k];
     __syncthreads();
+    if (w != 0) return;
+    double t[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) t[k] = warp_sum_d(red[lane][k]);              // the 32 warp sums: a second fixed-order tree
     if (threadIdx.x == 0) {
-        double t[7] = {0, 0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < 32; ++i)
-            for (int k = 0; k < 7; ++k) t[k] += red[i][k];
         const double RS = (double)R * (double)S;
         const float n_fs = (float)counts[0], n_sdf = (float)counts[1];
         const float n = (float)(counts[0] + counts[1]);
