@@ -69,10 +69,22 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def pause(self):
+        """Stops polling (the rows collected so far are kept); start() resumes."""
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.t.join(timeout=1.0)
+            except Exception:
+                pass
+            self.proc = None
+            self.started = True
+
     def stop(self):
-        if self.proc is None:
+        if self.proc is None and not getattr(self, "started", False):
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        self.proc.terminate()
+        if self.proc is not None:
+            self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -268,9 +280,11 @@ def run_gpu(args):
     e2e_val = timed_e2e(lambda: mapper.step_host(rays7, pose_idx, poses_d))
     h2d_bytes, d2h_bytes = rays7.numel() * 4 + pose_idx.numel() * 8, 8 * 4
 
-    # (the clock / throttle sampler has covered the device-timed regions and the GPU-bound loop above; it stops here because the
-    # nvidia-smi poll takes the driver lock every 50 ms, which the HOST-bound drop-in loop below would feel)
-    clocks = sampler.stop() if rank == 0 else None
+    # (the clock / throttle sampler has covered the device-timed regions and the GPU-bound loop above; it pauses here because the
+    # nvidia-smi poll takes the driver lock every 50 ms, which the HOST-bound drop-in loop below would feel, and resumes for the
+    # GPU-bound tracking / frame / joint-query measurements)
+    if rank == 0:
+        sampler.pause()
     model2 = H.cuda_model(cfg, H.state_of(of))
     opt = mf.create_map_optimizer(model2, cfg["mapping"]["lr_decoder"], cfg["mapping"]["lr_embed"])
     tw = cfg["training"]
@@ -292,6 +306,8 @@ def run_gpu(args):
         return float(loss.detach())                          # D2H read of the step's result
     e2e_autograd = timed_e2e(autograd_step)
     del model2, opt
+    if rank == 0:
+        sampler.start()
 
 
     # ---- tracking metric (BASELINE configs[1] shape): RandomOptimizer scoring 1024 candidates x 2048 pixels ----
@@ -310,6 +326,7 @@ def run_gpu(args):
         also.update(joint_query_bench(dev))
         also.update(store_bench(mapper, dev, args.steps))
         also.update(render_full_bench(dev))
+    clocks = sampler.stop() if rank == 0 else None          # (before the CPU baselines: only GPU-loaded intervals are sampled)
     also_roof = {k[len("_roof_"):]: also.pop(k) for k in [k for k in also if k.startswith("_roof_")]}
     also_roof = {k: v for k, v in also_roof.items() if v}
 
