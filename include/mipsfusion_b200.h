@@ -356,6 +356,25 @@ int mf_joint_query_accumulate(const mf_point_set* ps_host, const mf_submap* subm
  * fill value (-1 for sdf, 0 for rgb)  (Mesher.py:461,525-527). */
 int mf_joint_query_finalize(const float* acc, const uint8_t* mask_any, int color, int64_t g_count, float* out, void* stream);
 
+/* ---- N2: marching cubes on a dense SDF volume (external/NumpyMarchingCubes/marching_cubes/src/marching_cubes.cpp:418-462 =
+ * marching_cubes(volume, isovalue, truncation) of utils/utils.py:78,159; binding replaced: pywrapper.cpp:9-54) ----
+ * volume (nx,ny,nz) float32, C-contiguous, device (the reference reads each element as double and narrows it to float,
+ * marching_cubes.cpp:82; the host side does that cast).  Results are bit-identical to the reference: vertices in voxel units in
+ * the reference's order (first-come clusters on its 1e-5 lattice), faces in the i,j,k scan order with degenerate and duplicate
+ * faces removed.  Two calls because the output sizes are data dependent:
+ *   mf_mcubes_count : dual-node values, triangle count per cell and their scan offsets into `workspace`
+ *                     (mf_mcubes_count_workspace_size bytes); *n_tris (device) = triangles before merging.  Asynchronous.
+ *   mf_mcubes_mesh  : n_tris as read back by the caller; mesh_workspace of mf_mcubes_mesh_workspace_size(n_tris) bytes;
+ *                     verts capacity (3 n_tris, 3) float32, faces capacity (n_tris, 3) uint32; counts (device, 3 x int64) =
+ *                     {vertices, faces, clustering rounds}.  Synchronises `stream` once per clustering round (>= 1) and on return.
+ * truncation must be finite; dimensions < 2048. */
+int64_t mf_mcubes_count_workspace_size(int64_t nx, int64_t ny, int64_t nz);
+int mf_mcubes_count(const float* volume, int64_t nx, int64_t ny, int64_t nz, float isovalue, float truncation, void* workspace,
+                    int64_t* n_tris, void* stream);
+int64_t mf_mcubes_mesh_workspace_size(int64_t n_tris);
+int mf_mcubes_mesh(const void* count_workspace, int64_t nx, int64_t ny, int64_t nz, float isovalue, int64_t n_tris,
+                   void* mesh_workspace, float* verts, uint32_t* faces, int64_t* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

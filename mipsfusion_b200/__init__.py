@@ -18,3 +18,4 @@ from .tracker import FusedPoseRefiner  # noqa: F401
 from .submap_parallel import SubmapParallel  # noqa: F401
 from . import sampling_helper  # noqa: F401
 from .manager import SubmapContainment, pts_in_bbox  # noqa: F401
+from .marching_cubes import marching_cubes, marching_cubes_device  # noqa: F401

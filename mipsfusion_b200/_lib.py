@@ -111,6 +111,10 @@ PROTOTYPES = {
     "mf_joint_query_maxdist": (_I, [C.POINTER(PointSet), C.POINTER(Submap), _I, _L, _L, _P, _P]),
     "mf_joint_query_accumulate": (_I, [C.POINTER(PointSet), C.POINTER(Submap), _I, _I, _I, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P]),
     "mf_joint_query_finalize": (_I, [_P, _P, _I, _L, _P, _P]),
+    "mf_mcubes_count_workspace_size": (_L, [_L, _L, _L]),
+    "mf_mcubes_count": (_I, [_P, _L, _L, _L, C.c_float, C.c_float, _P, _P, _P]),
+    "mf_mcubes_mesh_workspace_size": (_L, [_L]),
+    "mf_mcubes_mesh": (_I, [_P, _L, _L, _L, C.c_float, _L, _P, _P, _P, _P, _P]),
 }
 
 _lib = None
