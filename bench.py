@@ -327,6 +327,7 @@ def run_gpu(args):
         also.update(store_bench(mapper, dev, args.steps))
         also.update(render_full_bench(dev))
         also.update(marching_cubes_bench(dev))
+        also.update(mesh_pipeline_bench(dev))
     clocks = sampler.stop() if rank == 0 else None          # (before the CPU baselines: only GPU-loaded intervals are sampled)
     also_roof = {k[len("_roof_"):]: also.pop(k) for k in [k for k in also if k.startswith("_roof_")]}
     also_roof = {k: v for k, v in also_roof.items() if v}
@@ -583,6 +584,27 @@ def mc_volume(n, dev):
     return torch.tanh(d * 12.0).contiguous()
 
 
+def mesh_pipeline_bench(dev, res=512, n_submaps=16):
+    """C5 end to end on the device: blended SDF over 512^3 x 16 submaps -> marching cubes -> blended vertex colours
+    (JointSubmapQuery.extract_mesh = Mesher.extract_mesh_jointly steps 4, 5 and 9).  The decoders are randomly initialised (no
+    checkpoints offline), so the surface is whatever level set the random field has; the work per grid point is the real one."""
+    import torch
+    jq, axes, _, _ = joint_query_setup(dev, res, n_submaps)
+    small = [a_[:96] for a_ in axes]
+    jq.extract_mesh(small)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = jq.extract_mesh(axes)                                   # allocations of the full-size buffers
+    del out
+    a.record()
+    out = jq.extract_mesh(axes)
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    return {"mesh_pipeline_ms": ms, "mesh_pipeline_grid_points_per_s": res ** 3 / (ms * 1e-3),
+            "mesh_pipeline": f"{res}^3 grid x {n_submaps} submaps -> blended SDF -> marching cubes ({out['vertices'].shape[0]} vertices, "
+                             f"{out['faces'].shape[0]} faces) -> blended vertex colours, device resident"}
+
+
 def marching_cubes_bench(dev, n=512):
     """marching cubes over the 512^3 blended-SDF grid of C5 (utils/utils.py:78 -> NumpyMarchingCubes), device
     volume in, device mesh out; the two C-ABI calls and their host read-backs of the data-dependent sizes are inside the events."""
@@ -757,9 +779,8 @@ def store_bench(mapper, dev, steps):
                                "mf_gen_rays_packed -> map step; no host data per step"}
 
 
-def joint_query_bench(dev, res=512, n_submaps=16, group=None, shard="points", prefix="joint_query"):
-    """BASELINE configs[4] shape: joint SDF grid query at res^3 over n_submaps submaps (Mesher / render_mesh path):
-    containment + world->submap transform + field query (sdf, entropy) + entropy/distance-weighted blend."""
+def joint_query_setup(dev, res=512, n_submaps=16):
+    """16 overlapping submap boxes (4 x 4 across x / y, full height) over the apartment-sized volume and the res^3 grid axes."""
     import numpy as np
     import torch
     import helpers as H
@@ -771,7 +792,7 @@ def joint_query_bench(dev, res=512, n_submaps=16, group=None, shard="points", pr
     models, poses, amin, amax, cents = [], [], [], [], []
     lo, hi = np.array([-0.6, 0.5, -1.15]), np.array([2.95, 7.05, 3.05])
     ext = hi - lo
-    for m in range(n_submaps):                                   # 4 x 4 overlapping boxes across x / y, full height
+    for m in range(n_submaps):
         ix, iy = m % 4, m // 4
         a = lo + ext * np.array([ix / 4.0 - 0.08, iy / 4.0 - 0.08, 0.0])
         b = lo + ext * np.array([(ix + 1) / 4.0 + 0.08, (iy + 1) / 4.0 + 0.08, 1.0])
@@ -779,7 +800,15 @@ def joint_query_bench(dev, res=512, n_submaps=16, group=None, shard="points", pr
         T = torch.eye(4); T[:3, 3] = torch.tensor((a + b) / 2, dtype=torch.float32)
         poses.append(T); amin.append(a); amax.append(b); cents.append(((a + b) / 2).astype(np.float32))
     axes = [np.linspace(lo[k], hi[k], res) for k in range(3)]
-    jq = mf.JointSubmapQuery(models, poses, amin, amax, cents)
+    return mf.JointSubmapQuery(models, poses, amin, amax, cents), axes, amin, amax
+
+
+def joint_query_bench(dev, res=512, n_submaps=16, group=None, shard="points", prefix="joint_query"):
+    """BASELINE configs[4] shape: joint SDF grid query at res^3 over n_submaps submaps (Mesher / render_mesh path):
+    containment + world->submap transform + field query (sdf, entropy) + entropy/distance-weighted blend."""
+    import numpy as np
+    import torch
+    jq, axes, amin, amax = joint_query_setup(dev, res, n_submaps)
     kw = {} if group is None else dict(group=group, shard=shard)
     jq.query(axes=[a_[:64] for a_ in axes], **kw)                # warm-up: kernels, ...
     out = jq.query(axes=axes, **kw)                              # ... and the 1.3 GB of result / work buffers (cudaMalloc is not the query)

@@ -2,9 +2,11 @@
 + blend part of reference model/Mesher.py:464-528 (geometry) and :606-663 (colour), fused into
 CUDA passes over a grid generated on the fly (no host arrays, no per-chunk .cpu().numpy()).
 
-Marching cubes, the open3d bounding geometry and mesh clean-up stay where they are in the reference
-(out of scope); this module hands back exactly the arrays they consume: the blended TSDF grid
-(-1 where no submap sees the point), the validity mask, and per-submap containment masks."""
+The open3d bounding geometry and mesh clean-up stay where they are in the reference (out of scope);
+``query`` hands back exactly the arrays they consume: the blended TSDF grid (-1 where no submap sees the
+point), the validity mask, and per-submap containment masks.  ``extract_mesh`` goes on to the surface
+on the device (marching cubes of ``marching_cubes.py``, then the blended vertex colours), so that the
+grid never visits the host."""
 import ctypes as C
 
 import numpy as np
@@ -109,3 +111,27 @@ class JointSubmapQuery:
         if contain is not None:
             res["contain"] = contain[:g_count].bool()
         return res
+
+    @torch.no_grad()
+    def extract_mesh(self, axes, isolevel=0.0, truncation=3.0, color=True, vis=None):
+        """Steps 4-5 (+ the colour query of step 9) of reference Mesher.extract_mesh_jointly (model/Mesher.py:464-540,606-663)
+        without leaving the device: blended SDF over the grid ``axes`` -> volume (nx, ny, nz) as Mesher.py:533 reshapes it ->
+        marching cubes -> vertices in world coordinates (voxel index * spacing + origin, Mesher.py:535-543) -> blended colours.
+        Grid points no submap contains are excluded from the surface the way the reference's ``mask=final_mask_mc`` does: they are
+        handed to marching cubes as -inf, which its voxel test rejects (marching_cubes.cpp:83).
+        The reference calls skimage's Lewiner marching cubes here (unpinned third-party package, absent offline); this route
+        uses the marching cubes the reference ships in-tree (NumpyMarchingCubes, utils/utils.py:78), bit-identical to it.
+        -> dict(vertices (V,3) float32 world, faces (F,3) int64, colors (V,3) float32 | None, sdf_volume (nx,ny,nz))"""
+        from .marching_cubes import marching_cubes_device
+        nx, ny, nz = (len(a) for a in axes)
+        r = self.query(axes=axes, vis=vis)
+        sdf = r["sdf"].masked_fill(~r["mask"], float("-inf"))
+        vol = sdf.reshape(ny, nx, nz).transpose(0, 1).contiguous()
+        verts, faces = marching_cubes_device(vol, isolevel, truncation)
+        origin = torch.tensor([axes[0][0], axes[1][0], axes[2][0]], dtype=torch.float64, device=verts.device)
+        spacing = torch.tensor([axes[k][2] - axes[k][1] for k in range(3)], dtype=torch.float64, device=verts.device)
+        world = verts.to(torch.float64) * spacing + origin
+        colors = None
+        if color and world.shape[0] > 0:
+            colors = self.query(points=world, color=True)["rgb"]
+        return {"vertices": world.to(torch.float32), "faces": faces, "colors": colors, "sdf_volume": vol}

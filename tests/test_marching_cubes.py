@@ -152,3 +152,34 @@ def test_cuda_full_size_properties():
     sv, sf = mf.marching_cubes_device(slab, 0.0, 3.0)
     ov, of_ = omc.marching_cubes(slab.cpu().numpy(), 0.0, 3.0)
     assert np.array_equal(sv.cpu().numpy().astype(np.float64), ov) and np.array_equal(sf.cpu().numpy().astype(np.uint64), of_)
+
+
+@pytest.mark.gpu
+def test_joint_query_extract_mesh_on_device():
+    """JointSubmapQuery.extract_mesh (query -> volume -> marching cubes -> vertex colours, all on the device): the mesh equals the
+    oracle's marching cubes run on the very volume the device produced (bit for bit), masked grid points carry -inf, the world
+    coordinates follow Mesher.py:535-543, and the colours equal a separate colour query at the vertices."""
+    import torch
+    import mipsfusion_b200 as mf
+    import helpers as H
+    from test_gpu_tracking_query import _submaps
+    cfg = H.make_config(12)
+    cfg["grid"]["use_bound_normalize"] = False
+    fields, models, poses, amin, amax, cents = _submaps(3, cfg)
+    axes = mf.get_grid_uniform(np.array([-0.2, 1.0, -0.6]), np.array([2.4, 4.8, 1.6]), voxel_size=0.09)
+    jq = mf.JointSubmapQuery(models, poses, amin, amax, cents)
+    out = jq.extract_mesh(axes)
+    vol = out["sdf_volume"].cpu().numpy()
+    assert vol.shape == tuple(len(a) for a in axes)
+    ref = jq.query(axes=axes)
+    nx, ny, nz = vol.shape
+    mask = ref["mask"].reshape(ny, nx, nz).transpose(0, 1).cpu().numpy()
+    assert np.all(np.isneginf(vol[~mask])) and np.all(np.isfinite(vol[mask])) and (~mask).any() and mask.any()
+    assert np.array_equal(vol[mask], ref["sdf"].reshape(ny, nx, nz).transpose(0, 1).cpu().numpy()[mask])
+    ov, of_ = omc.marching_cubes(vol, 0.0, 3.0)
+    assert of_.shape[0] > 100
+    assert np.array_equal(out["faces"].cpu().numpy().astype(np.uint64), of_)
+    origin = np.array([a[0] for a in axes]); spacing = np.array([a[2] - a[1] for a in axes])
+    assert np.allclose(out["vertices"].cpu().numpy(), (ov * spacing + origin).astype(np.float32), rtol=0, atol=1e-6)
+    col = jq.query(points=(ov * spacing + origin), color=True)["rgb"]
+    assert torch.equal(col, out["colors"]) and out["colors"].shape == (ov.shape[0], 3)
