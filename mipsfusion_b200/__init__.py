@@ -18,4 +18,5 @@ from .tracker import FusedPoseRefiner  # noqa: F401
 from .submap_parallel import SubmapParallel  # noqa: F401
 from . import sampling_helper  # noqa: F401
 from .manager import SubmapContainment, pts_in_bbox  # noqa: F401
-from .marching_cubes import marching_cubes, marching_cubes_device  # noqa: F401
+from . import marching_cubes  # noqa: F401  (module, like the reference's `marching_cubes` package: marching_cubes.marching_cubes(volume, isovalue, truncation))
+from .marching_cubes import marching_cubes_device  # noqa: F401

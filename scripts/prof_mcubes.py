@@ -29,5 +29,5 @@ from oracle import marching_cubes as omc   # noqa: E402
 sub = vol[:128, :128, :128].cpu().numpy()
 t = time.perf_counter(); ov, of_ = omc.marching_cubes(sub, 0.0, 3.0); dt = time.perf_counter() - t
 print(f"oracle 128^3: {dt:.3f} s = {128 ** 3 / dt / 1e6:.2f} M voxels/s, faces {of_.shape[0]}")
-sv, sf = mf.marching_cubes(sub, 0.0, 3.0)
+sv, sf = mf.marching_cubes.marching_cubes(sub, 0.0, 3.0)
 print("sub-volume parity:", np.array_equal(sv, ov) and np.array_equal(sf, of_))

@@ -75,7 +75,7 @@ def test_oracle_input_dtypes_and_errors():
 def test_cuda_matches_golden(golden):
     import mipsfusion_b200 as mf
     for name, vol, iso, trunc, gv, gf in _golden_cases(golden):
-        v, f = mf.marching_cubes(vol, iso, trunc)
+        v, f = mf.marching_cubes.marching_cubes(vol, iso, trunc)
         assert v.dtype == np.float64 and f.dtype == np.uint64
         assert _same((v, f), (gv.astype(np.float64), gf.astype(np.uint64))), name
 
@@ -107,19 +107,19 @@ def test_cuda_edge_cases():
     import mipsfusion_b200 as mf
     for shape in [(1, 1, 1), (2, 2, 2), (3, 3, 3), (2, 30, 30), (5, 3, 4)]:
         vol = mc_volumes.sphere(shape, [s / 2 for s in shape], 1.2)
-        v, f = mf.marching_cubes(vol, 0.0, 3.0)
+        v, f = mf.marching_cubes.marching_cubes(vol, 0.0, 3.0)
         ov, of_ = omc.marching_cubes(vol, 0.0, 3.0)
         assert _same((v, f), (ov, of_)), shape
-    v, f = mf.marching_cubes(np.full((16, 16, 16), -np.inf, np.float32), 0.0, 3.0)
+    v, f = mf.marching_cubes.marching_cubes(np.full((16, 16, 16), -np.inf, np.float32), 0.0, 3.0)
     assert v.shape == (0, 3) and f.shape == (0, 3)
     with pytest.raises(RuntimeError):
-        mf.marching_cubes(np.zeros((4, 4), np.float32), 0.0, 3.0)
+        mf.marching_cubes.marching_cubes(np.zeros((4, 4), np.float32), 0.0, 3.0)
     with pytest.raises(mf.MipsFusionB200Error):
-        mf.marching_cubes(np.zeros((4, 4, 4), np.float32), 0.0, float("inf"))
+        mf.marching_cubes.marching_cubes(np.zeros((4, 4, 4), np.float32), 0.0, float("inf"))
     # float64 input goes through the reference's double -> float narrowing
     vol = mc_volumes.sphere((20, 20, 20), (9.4, 9.9, 10.3), 6.0, noise=0.2, seed=3).astype(np.float64) + 1e-12
-    assert _same(mf.marching_cubes(vol, 0.0, 3.0), omc.marching_cubes(vol, 0.0, 3.0))
-    assert _same(mf.marching_cubes(torch.from_numpy(vol), 0.0, 3.0), omc.marching_cubes(vol, 0.0, 3.0))
+    assert _same(mf.marching_cubes.marching_cubes(vol, 0.0, 3.0), omc.marching_cubes(vol, 0.0, 3.0))
+    assert _same(mf.marching_cubes.marching_cubes(torch.from_numpy(vol), 0.0, 3.0), omc.marching_cubes(vol, 0.0, 3.0))
 
 
 @pytest.mark.gpu
