@@ -42,4 +42,12 @@ def cases():
     out["flat"] = (np.full((9, 9, 9), 0.5, np.float32), 0.0, 3.0)                                                   # no surface
     out["thin"] = (sphere((2, 12, 12), (0.5, 6, 6), 3.0), 0.0, 3.0)                                                 # no interior cell
     out["room"] = (room(32, seed=6), 0.0, 3.0)
+    # vertices 1e-5 .. 1e-4 away from cell corners: integer voxels give nodes on multiples of 1/8; with the level 1.2e-5 below
+    # 1.0 every node equal to 1.0 interpolates to mu = 1.2e-5 / (j / 8), i.e. 1-10 lattice steps from the corner along each of
+    # its edges -> ADJACENT lattice cells, chains of them, and representatives two steps apart (the order-dependent part of the
+    # reference's greedy clustering, marching_cubes.cpp:292-314,346-363)
+    ints = np.random.default_rng(8).integers(-2, 3, size=(22, 20, 21)).astype(np.float32)
+    out["lattice_chains"] = (ints, float(np.float32(1.0) - np.float32(1.2e-5)), 3.0)
+    out["lattice_chains_eighths"] = (np.random.default_rng(9).integers(-2, 3, size=(18, 18, 18)).astype(np.float32) * 0.125,
+                                     float(np.float32(0.125) - np.float32(1.1e-5)), 3.0)
     return out

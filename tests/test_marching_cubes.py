@@ -183,3 +183,29 @@ def test_joint_query_extract_mesh_on_device():
     assert np.allclose(out["vertices"].cpu().numpy(), (ov * spacing + origin).astype(np.float32), rtol=0, atol=1e-6)
     col = jq.query(points=(ov * spacing + origin), color=True)["rgb"]
     assert torch.equal(col, out["colors"]) and out["colors"].shape == (ov.shape[0], 3)
+
+
+@pytest.mark.gpu
+def test_cuda_greedy_clustering_chains():
+    """The order-dependent part of the reference's vertex clustering: volumes whose vertices fall into ADJACENT 1e-5 lattice cells
+    (see mc_volumes.cases()['lattice_chains']), at sizes where thousands of such chains exist.  The device resolves them as a
+    fixed point (possibly several rounds); the result must still be the sequential one, bit for bit."""
+    import torch
+    import mipsfusion_b200 as mf
+    _ensure_oracle()
+    rounds, chains = [], []
+    for seed, shape, step in [(31, (64, 60, 62), 1.0), (32, (80, 80, 80), 1.0), (33, (48, 50, 52), 0.5)]:
+        vol = np.random.default_rng(seed).integers(-2, 3, size=shape).astype(np.float32) * np.float32(step)
+        iso = float(np.float32(step) - np.float32(1.2e-5))
+        ov, of_ = omc.marching_cubes(vol, iso, 3.0)
+        dv, df, info = mf.marching_cubes_device(torch.from_numpy(vol).cuda(), iso, 3.0, return_info=True)
+        rounds.append(info["rounds"])
+        assert np.array_equal(dv.cpu().numpy().astype(np.float64), ov), (seed, info)
+        assert np.array_equal(df.cpu().numpy().astype(np.uint64), of_), (seed, info)
+        # the fixture does what it is meant to: representatives two lattice steps apart exist (chains through a merged cell)
+        k = (ov.astype(np.float32) / np.float32(1e-5) + np.float32(0.5) * np.sign(ov.astype(np.float32))).astype(np.int64)
+        keys = set(map(tuple, k[:30000]))
+        chains.append(sum((a + d[0], b + d[1], c + d[2]) in keys for (a, b, c) in keys
+                          for d in ((2, 0, 0), (0, 2, 0), (0, 0, 2), (1, 1, 0), (1, 0, 1), (0, 1, 1), (1, -1, 0), (1, 0, -1), (0, 1, -1))))
+    print("clustering rounds:", rounds, "representative pairs <= 2 lattice steps apart:", chains)
+    assert sum(chains) > 100, chains
