@@ -375,6 +375,17 @@ int64_t mf_mcubes_mesh_workspace_size(int64_t n_tris);
 int mf_mcubes_mesh(const void* count_workspace, int64_t nx, int64_t ny, int64_t nz, float isovalue, int64_t n_tris,
                    void* mesh_workspace, float* verts, uint32_t* faces, int64_t* counts, void* stream);
 
+/* ---- N2 (cont.): mesh visibility filter of the Mesher (model/Mesher.py:247-281 point_mask, :221-231 get_face_mask;
+ * helper_functions/geometry_helper.py:216-222 project_to_pixel) ----
+ * points (n,3) world; w2c (k,12): rows of the inverse keyframe poses [R | t]; max_depth (k): largest stored depth of each
+ * keyframe (Mesher.py:273); K (9) camera matrix, all fp32 device.  seen[i] = 1 iff for some keyframe the point projects
+ * strictly inside (edge, img_w - edge) x (edge, img_h - edge), has camera z < 0 and 0 < |z| < max_depth; fp32 in the
+ * reference's operation order (left-to-right sums of products, x negated before K, division by z + 1e-5).
+ * mf_mesh_face_mask: keep[f] = seen[a] | seen[b] | seen[c] (a face is dropped only if all three vertices are unseen). */
+int mf_mesh_seen_mask(const float* points, int64_t n, const float* w2c, const float* max_depth, int k, const float* K, int img_w,
+                      int img_h, int edge, uint8_t* seen, void* stream);
+int mf_mesh_face_mask(const uint8_t* seen, const int64_t* faces, int64_t n_faces, uint8_t* keep, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -115,6 +115,8 @@ PROTOTYPES = {
     "mf_mcubes_count": (_I, [_P, _L, _L, _L, C.c_float, C.c_float, _P, _P, _P]),
     "mf_mcubes_mesh_workspace_size": (_L, [_L]),
     "mf_mcubes_mesh": (_I, [_P, _L, _L, _L, C.c_float, _L, _P, _P, _P, _P, _P]),
+    "mf_mesh_seen_mask": (_I, [_P, _L, _P, _P, _I, _P, _I, _I, _I, _P, _P]),
+    "mf_mesh_face_mask": (_I, [_P, _P, _L, _P, _P]),
 }
 
 _lib = None

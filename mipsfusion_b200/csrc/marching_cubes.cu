@@ -654,3 +654,64 @@ MF_API int mf_mcubes_mesh(const void* count_workspace, int64_t nx, int64_t ny, i
     MF_CUDA(cudaStreamSynchronize(st));                                                 // (`rounds` is a stack variable)
     return MF_OK;
 }
+
+// ---- mesh visibility filter of the Mesher (model/Mesher.py:221-281; helper_functions/geometry_helper.py:216-222) ----
+// A vertex is seen if, for some keyframe, it projects more than `edge` pixels inside the image, lies in front of the camera
+// (camera z < 0) and nearer than the keyframe's largest stored depth.  fp32 in the reference's operation order (products, then
+// left-to-right sums, no contraction): cam = (p0 R00 + p1 R01) + p2 R02 + t; uv_h = K (-cam_x, cam_y, cam_z); uv = uv_h / (z_h + 1e-5).
+namespace {
+__global__ void mc_seen_mask_kernel(const float* __restrict__ pts, int64_t n, const float* __restrict__ w2c, const float* __restrict__ max_depth,
+                                    int k, const float* __restrict__ Kmat, float u_hi, float v_hi, float lo, uint8_t* __restrict__ seen) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float p0 = pts[3 * i], p1 = pts[3 * i + 1], p2 = pts[3 * i + 2];
+    float K9[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) K9[q] = __ldg(Kmat + q);
+    bool s = false;
+    for (int j = 0; j < k && !s; j++) {
+        const float* m = w2c + 12 * j;                            // rows of [R | t]
+        float c[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            c[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p0, __ldg(m + 4 * r)), __fmul_rn(p1, __ldg(m + 4 * r + 1))), __fmul_rn(p2, __ldg(m + 4 * r + 2))),
+                             __ldg(m + 4 * r + 3));
+        const float xn = -c[0];
+        float h[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            h[r] = __fadd_rn(__fadd_rn(__fmul_rn(K9[3 * r], xn), __fmul_rn(K9[3 * r + 1], c[1])), __fmul_rn(K9[3 * r + 2], c[2]));
+        const float zc = __fadd_rn(h[2], 1e-5f);
+        const float u = __fdiv_rn(h[0], zc), v = __fdiv_rn(h[1], zc);
+        const bool m1 = (u < u_hi) && (u > lo) && (v < v_hi) && (v > lo) && (c[2] < 0.0f);
+        const float cz = fabsf(c[2]);
+        s = m1 && (cz > 0.0f) && (cz < __ldg(max_depth + j));
+    }
+    seen[i] = s ? 1 : 0;
+}
+__global__ void mc_face_seen_kernel(const uint8_t* __restrict__ seen, const int64_t* __restrict__ faces, int64_t nf, uint8_t* __restrict__ keep) {
+    int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    keep[f] = (seen[faces[3 * f]] | seen[faces[3 * f + 1]] | seen[faces[3 * f + 2]]) ? 1 : 0;     // dropped only if ALL three are unseen
+}
+}  // namespace
+
+MF_API int mf_mesh_seen_mask(const float* points, int64_t n, const float* w2c, const float* max_depth, int k, const float* K, int img_w,
+                             int img_h, int edge, uint8_t* seen, void* stream) {
+    MF_CHECK_ARG(n >= 0 && k >= 0 && seen != nullptr);
+    if (n == 0) return MF_OK;
+    MF_CHECK_ARG(points != nullptr && K != nullptr && (k == 0 || (w2c != nullptr && max_depth != nullptr)));
+    mc_seen_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(points, n, w2c, max_depth, k, K, (float)(img_w - edge),
+                                                                                      (float)(img_h - edge), (float)edge, seen);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}
+
+MF_API int mf_mesh_face_mask(const uint8_t* seen, const int64_t* faces, int64_t n_faces, uint8_t* keep, void* stream) {
+    MF_CHECK_ARG(n_faces >= 0);
+    if (n_faces == 0) return MF_OK;
+    MF_CHECK_ARG(seen != nullptr && faces != nullptr && keep != nullptr);
+    mc_face_seen_kernel<<<(unsigned)((n_faces + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seen, faces, n_faces, keep);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}
