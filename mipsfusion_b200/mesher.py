@@ -22,6 +22,8 @@ class MeshVisibility:
         dev = points.device if points.is_cuda else torch.device("cuda")
         pts = L.f32c(points.reshape(-1, 3), dev)
         ids = torch.as_tensor(kf_Ids).to(torch.int64).cpu()
+        if ids.numel() == 0:                                                               # no keyframe: nothing is seen (Mesher.py:249)
+            return torch.zeros(pts.shape[0], device=dev, dtype=torch.bool)
         w2c = torch.as_tensor(kf_pose_c2w).to(torch.float32).inverse()[:, :3, :4]          # Mesher.py:252 (on the poses' own device)
         w2c = L.f32c(w2c.reshape(-1, 12), dev)
         depth = self.kf_rays[ids.to(self.kf_rays.device)][..., -1]
