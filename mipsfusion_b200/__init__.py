@@ -21,3 +21,4 @@ from .manager import SubmapContainment, pts_in_bbox  # noqa: F401
 from . import marching_cubes  # noqa: F401  (module, like the reference's `marching_cubes` package: marching_cubes.marching_cubes(volume, isovalue, truncation))
 from .marching_cubes import marching_cubes_device  # noqa: F401
 from .mesher import MeshVisibility  # noqa: F401
+from .mesh_utils import extract_mesh2, getVoxels  # noqa: F401

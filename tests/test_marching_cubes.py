@@ -209,3 +209,50 @@ def test_cuda_greedy_clustering_chains():
                           for d in ((2, 0, 0), (0, 2, 0), (0, 0, 2), (1, 1, 0), (1, 0, 1), (0, 1, 1), (1, -1, 0), (1, 0, -1), (0, 1, -1))))
     print("clustering rounds:", rounds, "representative pairs <= 2 lattice steps apart:", chains)
     assert sum(chains) > 100, chains
+
+
+@pytest.mark.gpu
+def test_extract_mesh2_on_device(tmp_path):
+    """extract_mesh2 (utils/utils.py:121-207, the caller of the in-tree marching cubes): the SDF volume against the oracle field
+    evaluated by the reference's composition on the CPU (1e-3), the mesh against the oracle's marching cubes on the device's own
+    volume pushed through the reference's vertex arithmetic (bit for bit), the colours against the oracle (1e-3), and the PLY."""
+    import torch
+    import mipsfusion_b200 as mf
+    import helpers as H
+    _ensure_oracle()
+    cfg = H.make_config(12)
+    cfg["data"]["translation"] = 0
+    of = H.oracle_field(cfg, grid_scale=0.5, seed=3)
+    model = H.cuda_model(cfg, H.state_of(of), train=False)
+    bb = torch.tensor(cfg["mapping"]["bound"], dtype=torch.float64)
+    c2w = torch.eye(4)
+    c2w[:3, :3] = torch.tensor([[0.9950042, -0.0998334, 0.0], [0.0998334, 0.9950042, 0.0], [0.0, 0.0, 1.0]])
+    c2w[:3, 3] = torch.tensor([0.05, -0.1, 0.02])
+    path = str(tmp_path / "mesh" / "submap.ply")
+    out = mf.extract_mesh2(model.query_sdf, c2w.cuda(), cfg, bb.cuda(), color_func=model.query_color, resolution=28, mesh_savepath=path,
+                           slab_points=5000)                                     # several slabs
+    tx, ty, tz = mf.getVoxels(bb[0, 1], bb[0, 0], bb[1, 1], bb[1, 0], bb[2, 1], bb[2, 0], None, 28)
+    q = torch.stack(torch.meshgrid(tx, ty, tz, indexing='ij'), -1).to(torch.float32)
+    w2l = c2w.inverse()
+    flat = (w2l[:3, :3] @ q.reshape(-1, 3).to(bb[:, 0]).to(w2l).T + w2l[:3, 3:]).T
+    flat = (flat - bb[:, 0]) / (bb[:, 1] - bb[:, 0])
+    with torch.no_grad():
+        vol_o = of.query_sdf(flat[:, None, :]).reshape(28, 28, 28).numpy()
+    vol = out["sdf_volume"].cpu().numpy()
+    assert H.rel_err(vol, vol_o) < 1e-3
+    ov, of_ = omc.marching_cubes(vol, 0.0, 3.0)
+    assert of_.shape[0] > 50 and np.array_equal(out["triangles"], of_)
+    v = ov.copy()
+    v /= np.array([[27, 27, 27]])
+    scale = np.array([tx.numpy()[-1] - tx.numpy()[0], ty.numpy()[-1] - ty.numpy()[0], tz.numpy()[-1] - tz.numpy()[0]])
+    v = scale[np.newaxis, :] * v + np.array([tx.numpy()[0], ty.numpy()[0], tz.numpy()[0]])
+    v = v / cfg["data"]["sc_factor"] - cfg["data"]["translation"]
+    assert np.array_equal(out["vertices"], v)
+    vl = (w2l[:3, :3] @ torch.from_numpy(v).to(bb).to(w2l).T + w2l[:3, 3:]).T
+    with torch.no_grad():
+        col_o = of.query_color(vl[:, None, :]).reshape(-1, 3).numpy()
+    assert H.rel_err(out["colors"], col_o) < 1e-3
+    raw = open(path, "rb").read()
+    head = raw[:raw.index(b"end_header\n") + 11].decode()
+    assert f"element vertex {v.shape[0]}" in head and f"element face {of_.shape[0]}" in head
+    assert len(raw) == len(head) + v.shape[0] * 16 + of_.shape[0] * 13
