@@ -624,7 +624,7 @@ def marching_cubes_bench(dev, n=512):
             "marching_cubes_mesh": f"{n}^3 volume -> {v.shape[0]} vertices, {f.shape[0]} faces ({info['soup_triangles']} triangles before "
                                    f"merging, {info['rounds']} clustering round(s)); bit-identical to the reference routine",
             "_roof_marching_cubes": {"alg_bytes": alg, "ms": ms, "achieved": alg / (ms * 1e-3) / 1e9,
-                                     "what": "whole call (13 kernels + 2 scans): 4 B per voxel read once + 12 B per output vertex and face"}}
+                                     "what": "whole call (15 kernels + 3 scans + 2 host read-backs of data-dependent sizes): 4 B per voxel read once + 12 B per output vertex and face"}}
 
 
 def render_full_bench(dev):
