@@ -6,7 +6,7 @@
 // greedily on a 1e-5 lattice in soup order (:316-390) and drops degenerate and duplicate faces (:246-288).  The sequential
 // parts are restated as order-free fixed points so that every step is a flat kernel:
 //   mc_nodes_kernel    corner ("dual node") values once per node instead of 8 x per cell; NaN marks an invalid node
-//   mc_classify_kernel triangle count per cell (u8) + per-256-cell block totals           } offsets = exclusive scan, which
+//   mc_classify_kernel triangle count per cell (u8) + totals per block of 1,024 cells      } offsets = exclusive scan, which
 //   mc_emit_kernel     triangle soup written at scan offsets -> the reference's order      } reproduces the i,j,k scan order
 //   mc_keys / mc_insert lattice key per soup vertex; open-addressing table keyed by the 96-bit lattice cell.  A slot stores only
 //                      the index of the vertex that claimed it (32-bit CAS); its key is re-read from keys[owner], so no
@@ -28,7 +28,7 @@
 namespace {
 
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
-constexpr int CB = 256;                 // cells per block in classify / emit
+constexpr int CB = 256;                 // threads per classify block (4 cells each: 1,024 cells per block)
 constexpr int SCAN_T = 512, SCAN_I = 8, SCAN_B = SCAN_T * SCAN_I;   // exclusive scan: 4096 items per block
 
 __device__ __forceinline__ bool voxel_valid(float d, float trunc) { return d != -INFINITY && fabsf(d) < trunc; }
