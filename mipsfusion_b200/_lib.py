@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmipsfusion_b200.so")
+LIB_PATH = os.environ.get("MIPSFUSION_B200_LIB") or os.path.join(_HERE, "libmipsfusion_b200.so")      # (override: A/B builds)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mipsfusion_b200.h")
 
 MF_MAX_LEVELS = 16

@@ -69,14 +69,32 @@ __device__ __forceinline__ void grid_corners(const float x[3], const LevelInfo& 
     for (int c = 0; c < 8; ++c) w[c] = __fmul_rn(__fmul_rn(wx[c & 1], wy[(c >> 1) & 1]), wz[(c >> 2) & 1]);
 }
 
+#ifndef MF_PAIR_GATHER
+#define MF_PAIR_GATHER 0
+#endif
 // Forward gather of one level: 8 corners, 2 features.  idx_out (8) optional.
 __device__ __forceinline__ float2 grid_level_fwd(const float x[3], const float2* __restrict__ grid2,
                                                  const LevelInfo& li, uint32_t* idx_out) {
     uint32_t idx[8]; float w[8];
     grid_corners(x, li, idx, w);
     float2 v[8];
+#if MF_PAIR_GATHER
+    // x-neighbours (idx[2k], idx[2k+1]) that are table neighbours on a 16-byte boundary (even x on a dense level without wrap,
+    // even x on a hashed level: (x + 1) ^ h = (x ^ h) ^ 1) come in with ONE 16-byte gather: fewer load wavefronts per point
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t i0 = idx[2 * k], i1 = idx[2 * k + 1];
+        if (((i0 & 1u) == 0u) && (i1 == i0 + 1u)) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(&grid2[li.offset + i0]));
+            v[2 * k] = make_float2(q.x, q.y); v[2 * k + 1] = make_float2(q.z, q.w);
+        } else {
+            v[2 * k] = __ldg(&grid2[li.offset + i0]); v[2 * k + 1] = __ldg(&grid2[li.offset + i1]);
+        }
+    }
+#else
 #pragma unroll
     for (int c = 0; c < 8; ++c) v[c] = __ldg(&grid2[li.offset + idx[c]]);     // 8 independent gathers in flight
+#endif
     float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
