@@ -163,7 +163,14 @@ def ptr(t):
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream():
+    """cudaStream_t of torch's current stream on the current device (the raw getter: building a torch.cuda.Stream object
+    per call costs several microseconds, and the drop-in training loop is host-bound)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -6,6 +6,7 @@ import contextlib
 import ctypes as C
 
 import torch
+import torch.optim.optimizer as _torch_opt
 
 from . import _lib as L
 
@@ -17,8 +18,22 @@ class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
 
-    @torch.no_grad()
+    def _patch_step_function(self):
+        """torch.optim.Optimizer wraps ``step`` in a profiler record_function + hook dispatcher (~10 us of host time per call,
+        which the host-bound drop-in loop feels).  ``step`` below goes through that wrapper only when a step hook is registered."""
+        self._zero_grad_profile_name = f"Optimizer.zero_grad#{self.__class__.__name__}.zero_grad"
+
     def step(self, closure=None, zero_grad=False):
+        if self._optimizer_step_pre_hooks or self._optimizer_step_post_hooks or _torch_opt._global_optimizer_pre_hooks \
+                or _torch_opt._global_optimizer_post_hooks:
+            hooked = self.__dict__.get("_hooked_step")
+            if hooked is None:
+                hooked = self.__dict__["_hooked_step"] = torch.optim.Optimizer.profile_hook_step(FusedAdam._step)
+            return hooked(self, closure, zero_grad=zero_grad)
+        return self._step(closure, zero_grad=zero_grad)
+
+    @torch.no_grad()
+    def _step(self, closure=None, zero_grad=False):
         """One Adam update.  zero_grad=True also clears every gradient in the same kernel pass
         (gradient tensors are kept, as with ``zero_grad(set_to_none=False)``)."""
         if zero_grad and self.__dict__.get("_map_model") is not None and self._step_map_model():
