@@ -193,6 +193,12 @@ int mf_render_loss_bwd(const float* raw, const float* z, const float* target_rgb
                        const int64_t* counts, const float* losses, const mf_render_cfg* cfg_host,
                        const float* g_losses, const float* g_rgb, const float* g_depth, float* d_raw,
                        int64_t R, int S, void* stream);
+/* The same with the four loss gradients as separate device scalars (NULL = 0): what autograd hands to the backward of a weighted
+ * sum of the four losses (mipsfusion.py:142-152), without packing them first. */
+int mf_render_loss_bwd_scalars(const float* raw, const float* z, const float* target_rgb, const float* target_d,
+                               const float* losses, const mf_render_cfg* cfg_host, const float* g_rgb_loss, const float* g_depth_loss,
+                               const float* g_sdf_loss, const float* g_fs_loss, const float* g_rgb, const float* g_depth,
+                               float* d_raw, int64_t R, int S, void* stream);
 
 /* ---- a10: dense Adam (torch.optim.Adam as configured at mipsfusion.py:580-584) ----
  * step >= 1; zero_grad != 0 also clears g (the reference's zero_grad, mipsfusion.py:335). */

@@ -256,10 +256,12 @@ __global__ void __launch_bounds__(1024) loss_finalize_kernel(const float* __rest
     }
 }
 
+struct LossGrads { const float* p[4]; };     // upstream gradients of rgb / depth / sdf / fs loss, each a device scalar or NULL (= 0)
+
 __global__ void __launch_bounds__(256) render_loss_bwd_kernel(
     const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ target_rgb,
     const float* __restrict__ target_d, const float* __restrict__ losses, RenderCfgDev c,
-    const float* __restrict__ g_losses, const float* __restrict__ g_rgb, const float* __restrict__ g_depth,
+    LossGrads g_losses, const float* __restrict__ g_rgb, const float* __restrict__ g_depth,
     float* __restrict__ d_raw, int64_t R, int S) {
     const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -289,8 +291,8 @@ __global__ void __launch_bounds__(256) render_loss_bwd_kernel(
     const float d = has_t ? target_d[r] : 0.f;
     const bool valid = has_t && d > 0.f && d < c.depth_trunc;
     const float mk = (valid || c.rgb_missing_nz) ? 1.f : 0.f;
-    const float gl_rgb = g_losses ? g_losses[0] : 0.f, gl_depth = g_losses ? g_losses[1] : 0.f;
-    const float gl_sdf = g_losses ? g_losses[2] : 0.f, gl_fs = g_losses ? g_losses[3] : 0.f;
+    const float gl_rgb = g_losses.p[0] ? __ldg(g_losses.p[0]) : 0.f, gl_depth = g_losses.p[1] ? __ldg(g_losses.p[1]) : 0.f;
+    const float gl_sdf = g_losses.p[2] ? __ldg(g_losses.p[2]) : 0.f, gl_fs = g_losses.p[3] ? __ldg(g_losses.p[3]) : 0.f;
     float G_rgb[3], G_depth = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -451,20 +453,37 @@ MF_API int mf_render_loss_fwd(const float* raw, const float* z, const float* tar
     return MF_OK;
 }
 
+static int render_loss_bwd_launch(const float* raw, const float* z, const float* target_rgb, const float* target_d,
+                                  const float* losses, const mf_render_cfg* cfg, LossGrads gl, const float* g_rgb,
+                                  const float* g_depth, float* d_raw, int64_t R, int S, void* stream, const char* fn) {
+    if (!(cfg && raw && z && d_raw && R >= 0 && (((uintptr_t)d_raw & 7) == 0) && S > 0 && S <= MAX_S && (!target_d || losses))) {
+        mf_set_error("%s: invalid argument", fn);
+        return MF_ERR_INVALID;
+    }
+    if (R == 0) return MF_OK;
+    const RenderCfgDev c = cfg_to_dev(cfg);
+    render_loss_bwd_kernel<<<(unsigned)((R + 7) / 8), 256, 0, (cudaStream_t)stream>>>(raw, z, target_rgb, target_d, losses, c, gl, g_rgb,
+                                                                                     g_depth, d_raw, R, S);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+}
+
 MF_API int mf_render_loss_bwd(const float* raw, const float* z, const float* target_rgb, const float* target_d,
                               const int64_t* counts, const float* losses, const mf_render_cfg* cfg, const float* g_losses,
                               const float* g_rgb, const float* g_depth, float* d_raw, int64_t R, int S, void* stream) {
     (void)counts;
-    MF_CHECK_ARG(cfg && raw && z && d_raw && R >= 0);
-    MF_CHECK_ARG(((uintptr_t)d_raw & 7) == 0);                 // 8-byte stores
-    MF_CHECK_ARG(S > 0 && S <= MAX_S);
-    if (R == 0) return MF_OK;
-    MF_CHECK_ARG(!target_d || losses);
-    const RenderCfgDev c = cfg_to_dev(cfg);
-    render_loss_bwd_kernel<<<(unsigned)((R + 7) / 8), 256, 0, (cudaStream_t)stream>>>(raw, z, target_rgb, target_d, losses, c,
-                                                                                     g_losses, g_rgb, g_depth, d_raw, R, S);
-    MF_LAUNCH_CHECK();
-    return MF_OK;
+    LossGrads gl;
+    for (int i = 0; i < 4; ++i) gl.p[i] = g_losses ? g_losses + i : nullptr;
+    return render_loss_bwd_launch(raw, z, target_rgb, target_d, losses, cfg, gl, g_rgb, g_depth, d_raw, R, S, stream, __func__);
+}
+
+MF_API int mf_render_loss_bwd_scalars(const float* raw, const float* z, const float* target_rgb, const float* target_d,
+                                      const float* losses, const mf_render_cfg* cfg, const float* g_rgb_loss, const float* g_depth_loss,
+                                      const float* g_sdf_loss, const float* g_fs_loss, const float* g_rgb, const float* g_depth,
+                                      float* d_raw, int64_t R, int S, void* stream) {
+    LossGrads gl;
+    gl.p[0] = g_rgb_loss; gl.p[1] = g_depth_loss; gl.p[2] = g_sdf_loss; gl.p[3] = g_fs_loss;
+    return render_loss_bwd_launch(raw, z, target_rgb, target_d, losses, cfg, gl, g_rgb, g_depth, d_raw, R, S, stream, __func__);
 }
 
 MF_API int mf_gen_rays(const float* dirs_cam, const float* poses, const int64_t* pose_idx, float* rays_o, float* rays_d,

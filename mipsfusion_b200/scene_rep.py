@@ -155,16 +155,20 @@ class _RenderFn(torch.autograd.Function):
         st = L.stream()
         field = model._field(ctx.keep, impl=ctx.impl)
         d_raw = torch.empty_like(raw)
-        gl = None
-        if not (g_l0 is None and g_l1 is None and g_l2 is None and g_l3 is None):
+        g_rgb = g_rgb.contiguous() if g_rgb is not None else None
+        g_depth = g_depth.contiguous() if g_depth is not None else None
+        gls = (g_l0, g_l1, g_l2, g_l3)
+        if all(g is None or (g.dtype == torch.float32 and g.is_cuda and g.numel() == 1) for g in gls):
+            # the four upstream loss gradients go to the kernel as they arrive (device scalars; None = 0): no packing kernel
+            L.call("mf_render_loss_bwd_scalars", L.ptr(raw), L.ptr(z), L.ptr(target_rgb), L.ptr(target_d), L.ptr(losses), C.byref(cfg),
+                   *[None if g is None else g.data_ptr() for g in gls], L.ptr(g_rgb), L.ptr(g_depth), L.ptr(d_raw), R, S, st)
+        else:
             zero = _ZERO.get(dev)
             if zero is None:
                 zero = _ZERO[dev] = torch.zeros((), device=dev, dtype=torch.float32)
-            gl = torch.stack([zero if g is None else g.reshape(()) for g in (g_l0, g_l1, g_l2, g_l3)]).to(torch.float32)
-        g_rgb = g_rgb.contiguous() if g_rgb is not None else None
-        g_depth = g_depth.contiguous() if g_depth is not None else None
-        L.call("mf_render_loss_bwd", L.ptr(raw), L.ptr(z), L.ptr(target_rgb), L.ptr(target_d), L.ptr(counts), L.ptr(losses),
-               C.byref(cfg), L.ptr(gl), L.ptr(g_rgb), L.ptr(g_depth), L.ptr(d_raw), R, S, st)
+            gl = torch.stack([zero if g is None else g.reshape(()) for g in gls]).to(torch.float32)
+            L.call("mf_render_loss_bwd", L.ptr(raw), L.ptr(z), L.ptr(target_rgb), L.ptr(target_d), L.ptr(counts), L.ptr(losses),
+                   C.byref(cfg), L.ptr(gl), L.ptr(g_rgb), L.ptr(g_depth), L.ptr(d_raw), R, S, st)
         if g_raw is not None:
             d_raw = d_raw + g_raw
         want_rays = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
