@@ -5,4 +5,3 @@ import json
 d=json.loads(open('gpurun_out/r2b_bench_8gpu.json').read().strip().splitlines()[-1])
 a=d['also']; print(d['value'], d['ms_per_step'], d['e2e']['value'], a['tracking_pose_candidates_per_s'], a['joint_query_s'], a['joint_query_submap_sharded_s'], a.get('c4_ms_per_frame_rank0'))
 PY
-tail -2 gpurun_out/r2b_bench_8gpu.err | cut -c1-300
