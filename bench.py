@@ -421,14 +421,14 @@ def tracking_bench(model, cfg, dev, iters=5, group=None):
     import torch
     import mipsfusion_b200 as mf
     from mipsfusion_b200 import synth
-    from oracle import sampling as osamp
+    from mipsfusion_b200.sampling_helper import sample_pixels_uniformly        # (the product's own lattice kernel: the oracle stays in the CPU legs)
     Cn, nr, nc = 1024, 32, 64
     tcfg = dict(cfg)
     tcfg["tracking"] = {"RO": {"particle_size": Cn, "initial_scaling_factor": 0.02, "rescaling_factor": 0.5, "n_rows": nr, "n_cols": nc},
                         "ignore_edge_W": 20, "ignore_edge_H": 20}
     dirs = synth.camera_rays()
     c2w = synth.trajectory(4)[1]
-    rows, cols = osamp.sample_pixels_uniformly(460, 620, nr, nc)
+    rows, cols = (t.cpu() for t in sample_pixels_uniformly(460, 620, nr, nc, device=dev))
     sub = synth.render_frame(c2w, dirs[rows, cols][None].contiguous())
     ds = types.SimpleNamespace(H=460, W=620, fx=320.0, fy=320.0, cx=309.5, cy=229.5, rays_d=dirs)
     g = torch.Generator().manual_seed(0)
