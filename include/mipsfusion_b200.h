@@ -187,6 +187,14 @@ int mf_render_loss_fwd(const float* raw, const float* z, const float* target_rgb
                        const int64_t* counts, const mf_render_cfg* cfg_host, float* out_rgb, float* out_depth,
                        float* out_aux, float* out_weights, int32_t* inds, float* losses, float* scratch,
                        int64_t R, int S, void* stream);
+/* _ld variants: target_rgb / target_d are R rows with row strides ld_rgb >= 3 / ld_d >= 1 floats -- the column slices the
+ * reference's loop takes out of its (R,10) batch tensor (mipsfusion.py:316-322) are read in place, without a copy each. */
+int mf_sample_z_ld(const float* target_d, int ld_d, const float* u, const float* lin_uniform, const float* lin_range,
+                   const float* lin_fallback, const mf_render_cfg* cfg_host, float* z, int64_t* counts, int64_t R, void* stream);
+int mf_render_loss_fwd_ld(const float* raw, const float* z, const float* target_rgb, int ld_rgb, const float* target_d, int ld_d,
+                          const int64_t* counts, const mf_render_cfg* cfg_host, float* out_rgb, float* out_depth,
+                          float* out_aux, float* out_weights, int32_t* inds, float* losses, float* scratch,
+                          int64_t R, int S, void* stream);
 /* g_losses (4) upstream grads of rgb/depth/sdf/fs loss (device); g_rgb (R,3) / g_depth (R) optional upstream
  * grads of the rendered maps -> d_raw (R,S,10). */
 int mf_render_loss_bwd(const float* raw, const float* z, const float* target_rgb, const float* target_d,
@@ -194,8 +202,8 @@ int mf_render_loss_bwd(const float* raw, const float* z, const float* target_rgb
                        const float* g_losses, const float* g_rgb, const float* g_depth, float* d_raw,
                        int64_t R, int S, void* stream);
 /* The same with the four loss gradients as separate device scalars (NULL = 0): what autograd hands to the backward of a weighted
- * sum of the four losses (mipsfusion.py:142-152), without packing them first. */
-int mf_render_loss_bwd_scalars(const float* raw, const float* z, const float* target_rgb, const float* target_d,
+ * sum of the four losses (mipsfusion.py:142-152), without packing them first; target row strides as in the _ld variants below. */
+int mf_render_loss_bwd_scalars(const float* raw, const float* z, const float* target_rgb, int ld_rgb, const float* target_d, int ld_d,
                                const float* losses, const mf_render_cfg* cfg_host, const float* g_rgb_loss, const float* g_depth_loss,
                                const float* g_sdf_loss, const float* g_fs_loss, const float* g_rgb, const float* g_depth,
                                float* d_raw, int64_t R, int S, void* stream);

@@ -86,7 +86,9 @@ PROTOTYPES = {
     "mf_field_query_rays_bwd": (_I, [_P, _P, _P, C.POINTER(Field), _P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
     "mf_render_loss_fwd": (_I, [_P, _P, _P, _P, _P, C.POINTER(RenderCfg), _P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
     "mf_render_loss_bwd": (_I, [_P, _P, _P, _P, _P, _P, C.POINTER(RenderCfg), _P, _P, _P, _P, _L, _I, _P]),
-    "mf_render_loss_bwd_scalars": (_I, [_P, _P, _P, _P, _P, C.POINTER(RenderCfg), _P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
+    "mf_render_loss_bwd_scalars": (_I, [_P, _P, _P, _I, _P, _I, _P, C.POINTER(RenderCfg), _P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
+    "mf_sample_z_ld": (_I, [_P, _I, _P, _P, _P, _P, C.POINTER(RenderCfg), _P, _P, _L, _P]),
+    "mf_render_loss_fwd_ld": (_I, [_P, _P, _P, _I, _P, _I, _P, C.POINTER(RenderCfg), _P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
     "mf_adam_step": (_I, [_P, _P, _P, _P, _L, _D, _D, _D, _D, _D, _I, _I, _P]),
     "mf_adam_step_sharded": (_I, [_P, _I, _I, _L, _L, _L, _P, _P, _L, _D, _D, _D, _D, _D, _I, C.c_uint64, _P]),
     "mf_adam_step_pair": (_I, [_P, _P, _P, _P, _L, _D, _D, _D, _P, _P, _P, _P, _L, _D, _D, _D, _D, _D, _I, _P]),

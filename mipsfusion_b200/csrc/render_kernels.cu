@@ -16,6 +16,8 @@ struct RenderCfgDev {
     float twoT;        // fp32(2 * truncation)
     float depth_trunc;
     float emd_w;
+    int ld_rgb, ld_d;  // row strides (floats) of target_rgb / target_d: 3 / 1 for contiguous tensors, 10 / 10 for column slices of
+                       // the reference loop's (R,10) batch tensor (mipsfusion.py:316-322), which then need no copy
 };
 
 static RenderCfgDev cfg_to_dev(const mf_render_cfg* c) {
@@ -25,6 +27,7 @@ static RenderCfgDev cfg_to_dev(const mf_render_cfg* c) {
     const double T = c->trunc * c->sc_factor;
     d.T = (float)T; d.twoT = (float)(2.0 * T);
     d.depth_trunc = (float)c->depth_trunc; d.emd_w = (float)c->emd_w;
+    d.ld_rgb = 3; d.ld_d = 1;
     return d;
 }
 
@@ -41,7 +44,7 @@ __global__ void sample_z_kernel(const float* __restrict__ target_d, const float*
     const int64_t r = blockIdx.x;
     const int S = c.n_u + c.n_r;
     const bool has_d = target_d != nullptr;
-    const float d = has_d ? target_d[r] : 0.f;
+    const float d = has_d ? target_d[r * c.ld_d] : 0.f;
     const bool around = d > 0.f;                      // rows with target_d <= 0 fall back to linspace(near, far)
     if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
     for (int e = threadIdx.x; e < S; e += blockDim.x) {
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(256) render_loss_fwd_kernel(
     }
     if (!target_d) return;
     // ---- loss partial sums of this ray (helper_functions/utils.py:71-111, scene_rep.py:211-226) ----
-    const float d = target_d[r];
+    const float d = target_d[r * c.ld_d];
     const bool valid = d > 0.f && d < c.depth_trunc;
     const float mk = (valid || c.rgb_missing_nz) ? 1.f : 0.f;
     float fs2 = 0.f, sdf2 = 0.f, fs1 = 0.f, sdf1 = 0.f;
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(256) render_loss_fwd_kernel(
         float rs = 0.f;
         if (target_rgb)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { const float e = rgb[k] * mk - target_rgb[r * 3 + k] * mk; rs = fmaf(e, e, rs); }
+            for (int k = 0; k < 3; ++k) { const float e = rgb[k] * mk - target_rgb[r * c.ld_rgb + k] * mk; rs = fmaf(e, e, rs); }
         float* sc = scratch + r * 8;
         sc[0] = rs; sc[1] = valid ? (depth - d) * (depth - d) : 0.f; sc[2] = valid ? 1.f : 0.f;
         sc[3] = fs2; sc[4] = sdf2; sc[5] = fs1; sc[6] = sdf1; sc[7] = 0.f;
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(256) render_loss_bwd_kernel(
     depth = warp_sum(depth);
     // upstream gradients of the rendered maps
     const bool has_t = target_d != nullptr;
-    const float d = has_t ? target_d[r] : 0.f;
+    const float d = has_t ? target_d[r * c.ld_d] : 0.f;
     const bool valid = has_t && d > 0.f && d < c.depth_trunc;
     const float mk = (valid || c.rgb_missing_nz) ? 1.f : 0.f;
     const float gl_rgb = g_losses.p[0] ? __ldg(g_losses.p[0]) : 0.f, gl_depth = g_losses.p[1] ? __ldg(g_losses.p[1]) : 0.f;
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(256) render_loss_bwd_kernel(
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         G_rgb[k] = g_rgb ? g_rgb[r * 3 + k] : 0.f;
-        if (has_t && target_rgb) G_rgb[k] += gl_rgb * 2.0f * mk * (rgb[k] * mk - target_rgb[r * 3 + k] * mk) / (3.0f * (float)R);
+        if (has_t && target_rgb) G_rgb[k] += gl_rgb * 2.0f * mk * (rgb[k] * mk - target_rgb[r * c.ld_rgb + k] * mk) / (3.0f * (float)R);
     }
     if (g_depth) G_depth = g_depth[r];
     if (valid && gl_depth != 0.f) G_depth += gl_depth * 2.0f * (depth - d) / losses[7];
@@ -415,9 +418,15 @@ __global__ void __launch_bounds__(256) gen_rays_bwd_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------
 MF_API int mf_sample_z(const float* target_d, const float* u, const float* lin_uniform, const float* lin_range,
                        const float* lin_fallback, const mf_render_cfg* cfg, float* z, int64_t* counts, int64_t R, void* stream) {
-    MF_CHECK_ARG(cfg && z && R >= 0);
+    return mf_sample_z_ld(target_d, 1, u, lin_uniform, lin_range, lin_fallback, cfg, z, counts, R, stream);
+}
+
+MF_API int mf_sample_z_ld(const float* target_d, int ld_d, const float* u, const float* lin_uniform, const float* lin_range,
+                          const float* lin_fallback, const mf_render_cfg* cfg, float* z, int64_t* counts, int64_t R, void* stream) {
+    MF_CHECK_ARG(cfg && z && R >= 0 && ld_d >= 1);
     if (R == 0) return MF_OK;
     RenderCfgDev c = cfg_to_dev(cfg);
+    c.ld_d = ld_d;
     if (!target_d) c.n_r = 0;
     const int S = c.n_u + c.n_r;
     MF_CHECK_ARG(S > 0 && S <= 4096);
@@ -437,11 +446,20 @@ MF_API int mf_render_loss_fwd(const float* raw, const float* z, const float* tar
                               const int64_t* counts, const mf_render_cfg* cfg, float* out_rgb, float* out_depth,
                               float* out_aux, float* out_weights, int32_t* inds, float* losses, float* scratch, int64_t R, int S,
                               void* stream) {
-    MF_CHECK_ARG(cfg && raw && z && out_rgb && out_depth && R >= 0);
+    return mf_render_loss_fwd_ld(raw, z, target_rgb, 3, target_d, 1, counts, cfg, out_rgb, out_depth, out_aux, out_weights, inds, losses,
+                                 scratch, R, S, stream);
+}
+
+MF_API int mf_render_loss_fwd_ld(const float* raw, const float* z, const float* target_rgb, int ld_rgb, const float* target_d, int ld_d,
+                                 const int64_t* counts, const mf_render_cfg* cfg, float* out_rgb, float* out_depth,
+                                 float* out_aux, float* out_weights, int32_t* inds, float* losses, float* scratch, int64_t R, int S,
+                                 void* stream) {
+    MF_CHECK_ARG(cfg && raw && z && out_rgb && out_depth && R >= 0 && ld_rgb >= 3 && ld_d >= 1);
     MF_CHECK_ARG(S > 0 && S <= MAX_S);
     if (R == 0) return MF_OK;
     MF_CHECK_ARG(!target_d || (counts && losses && scratch));
-    const RenderCfgDev c = cfg_to_dev(cfg);
+    RenderCfgDev c = cfg_to_dev(cfg);
+    c.ld_rgb = ld_rgb; c.ld_d = ld_d;
     cudaStream_t st = (cudaStream_t)stream;
     render_loss_fwd_kernel<<<(unsigned)((R + 7) / 8), 256, 0, st>>>(raw, z, target_rgb, target_d, c, out_rgb, out_depth, out_aux,
                                                                    out_weights, inds, scratch, R, S);
@@ -455,13 +473,15 @@ MF_API int mf_render_loss_fwd(const float* raw, const float* z, const float* tar
 
 static int render_loss_bwd_launch(const float* raw, const float* z, const float* target_rgb, const float* target_d,
                                   const float* losses, const mf_render_cfg* cfg, LossGrads gl, const float* g_rgb,
-                                  const float* g_depth, float* d_raw, int64_t R, int S, void* stream, const char* fn) {
-    if (!(cfg && raw && z && d_raw && R >= 0 && (((uintptr_t)d_raw & 7) == 0) && S > 0 && S <= MAX_S && (!target_d || losses))) {
+                                  const float* g_depth, float* d_raw, int64_t R, int S, void* stream, const char* fn, int ld_rgb = 3,
+                                  int ld_d = 1) {
+    if (!(cfg && raw && z && d_raw && R >= 0 && ld_rgb >= 3 && ld_d >= 1 && (((uintptr_t)d_raw & 7) == 0) && S > 0 && S <= MAX_S && (!target_d || losses))) {
         mf_set_error("%s: invalid argument", fn);
         return MF_ERR_INVALID;
     }
     if (R == 0) return MF_OK;
-    const RenderCfgDev c = cfg_to_dev(cfg);
+    RenderCfgDev c = cfg_to_dev(cfg);
+    c.ld_rgb = ld_rgb; c.ld_d = ld_d;
     render_loss_bwd_kernel<<<(unsigned)((R + 7) / 8), 256, 0, (cudaStream_t)stream>>>(raw, z, target_rgb, target_d, losses, c, gl, g_rgb,
                                                                                      g_depth, d_raw, R, S);
     MF_LAUNCH_CHECK();
@@ -477,13 +497,13 @@ MF_API int mf_render_loss_bwd(const float* raw, const float* z, const float* tar
     return render_loss_bwd_launch(raw, z, target_rgb, target_d, losses, cfg, gl, g_rgb, g_depth, d_raw, R, S, stream, __func__);
 }
 
-MF_API int mf_render_loss_bwd_scalars(const float* raw, const float* z, const float* target_rgb, const float* target_d,
+MF_API int mf_render_loss_bwd_scalars(const float* raw, const float* z, const float* target_rgb, int ld_rgb, const float* target_d, int ld_d,
                                       const float* losses, const mf_render_cfg* cfg, const float* g_rgb_loss, const float* g_depth_loss,
                                       const float* g_sdf_loss, const float* g_fs_loss, const float* g_rgb, const float* g_depth,
                                       float* d_raw, int64_t R, int S, void* stream) {
     LossGrads gl;
     gl.p[0] = g_rgb_loss; gl.p[1] = g_depth_loss; gl.p[2] = g_sdf_loss; gl.p[3] = g_fs_loss;
-    return render_loss_bwd_launch(raw, z, target_rgb, target_d, losses, cfg, gl, g_rgb, g_depth, d_raw, R, S, stream, __func__);
+    return render_loss_bwd_launch(raw, z, target_rgb, target_d, losses, cfg, gl, g_rgb, g_depth, d_raw, R, S, stream, __func__, ld_rgb, ld_d);
 }
 
 MF_API int mf_gen_rays(const float* dirs_cam, const float* poses, const int64_t* pose_idx, float* rays_o, float* rays_d,

@@ -95,6 +95,17 @@ def _grad_targets(model, grid, dev, need_grid, need_mlp):
     return g_grid, ret_grid, torch.zeros(L.MF_MLP_PARAMS, device=dev, dtype=torch.float32), True
 
 
+def _row_view(t, dev, R, w):
+    """fp32 device tensor of R rows x w columns with unit column stride (any row stride >= w): usable in place."""
+    return (t.dtype == torch.float32 and t.device == dev and t.dim() == 2 and t.shape[0] == R and t.shape[1] == w and R > 0
+            and (w == 1 or t.stride(1) == 1) and t.stride(0) >= w and t.data_ptr() % 4 == 0)
+
+
+def _ld(t, w):
+    """Row stride (floats) of a target tensor: contiguous (R,), (R,1) or (R,w), or a row-strided view accepted by _row_view."""
+    return w if (t is None or t.dim() == 1) else int(t.stride(0))
+
+
 _ZERO = {}                                      # device -> cached 0-dim zero (stand-in for an undefined loss gradient)
 
 
@@ -120,7 +131,10 @@ class _RenderFn(torch.autograd.Function):
         st = L.stream()
         z = torch.empty(R, S, device=dev, dtype=torch.float32)
         counts = torch.empty(2, device=dev, dtype=torch.int64)
-        L.call("mf_sample_z", L.ptr(target_d), L.ptr(u), L.ptr(lins[0]), L.ptr(lins[1]), L.ptr(lins[2]), C.byref(cfg), L.ptr(z),
+        ld_d, ld_rgb = _ld(target_d, 1), _ld(target_rgb, 3)
+        p_d = None if target_d is None else target_d.data_ptr()
+        p_rgb = None if target_rgb is None else target_rgb.data_ptr()
+        L.call("mf_sample_z_ld", p_d, ld_d, L.ptr(u), L.ptr(lins[0]), L.ptr(lins[1]), L.ptr(lins[2]), C.byref(cfg), L.ptr(z),
                L.ptr(counts), R, st)
         raw = torch.empty(R, S, L.MF_RAW_DIM, device=dev, dtype=torch.float32)
         # encoded-feature cache for the backward (tensor-core route, only when a backward can follow)
@@ -135,7 +149,7 @@ class _RenderFn(torch.autograd.Function):
         # (the loss kernels write all eight entries when targets are given)
         losses = torch.empty(8, device=dev, dtype=torch.float32) if target_d is not None else torch.zeros(8, device=dev, dtype=torch.float32)
         scratch = torch.empty(R * 8, device=dev, dtype=torch.float32) if target_d is not None else None
-        L.call("mf_render_loss_fwd", L.ptr(raw), L.ptr(z), L.ptr(target_rgb), L.ptr(target_d), L.ptr(counts), C.byref(cfg),
+        L.call("mf_render_loss_fwd_ld", L.ptr(raw), L.ptr(z), p_rgb, ld_rgb, p_d, ld_d, L.ptr(counts), C.byref(cfg),
                L.ptr(rgb), L.ptr(depth), L.ptr(aux), None, None, L.ptr(losses), L.ptr(scratch), R, S, st)
         ctx.model, ctx.cfg, ctx.S = model, cfg, S
         ctx.keep = field._keepalive
@@ -160,13 +174,16 @@ class _RenderFn(torch.autograd.Function):
         gls = (g_l0, g_l1, g_l2, g_l3)
         if all(g is None or (g.dtype == torch.float32 and g.is_cuda and g.numel() == 1) for g in gls):
             # the four upstream loss gradients go to the kernel as they arrive (device scalars; None = 0): no packing kernel
-            L.call("mf_render_loss_bwd_scalars", L.ptr(raw), L.ptr(z), L.ptr(target_rgb), L.ptr(target_d), L.ptr(losses), C.byref(cfg),
+            L.call("mf_render_loss_bwd_scalars", L.ptr(raw), L.ptr(z), None if target_rgb is None else target_rgb.data_ptr(), _ld(target_rgb, 3),
+                   None if target_d is None else target_d.data_ptr(), _ld(target_d, 1), L.ptr(losses), C.byref(cfg),
                    *[None if g is None else g.data_ptr() for g in gls], L.ptr(g_rgb), L.ptr(g_depth), L.ptr(d_raw), R, S, st)
         else:
             zero = _ZERO.get(dev)
             if zero is None:
                 zero = _ZERO[dev] = torch.zeros((), device=dev, dtype=torch.float32)
             gl = torch.stack([zero if g is None else g.reshape(()) for g in gls]).to(torch.float32)
+            target_rgb = None if target_rgb is None else target_rgb.contiguous()
+            target_d = None if target_d is None else target_d.contiguous()
             L.call("mf_render_loss_bwd", L.ptr(raw), L.ptr(z), L.ptr(target_rgb), L.ptr(target_d), L.ptr(counts), L.ptr(losses),
                    C.byref(cfg), L.ptr(gl), L.ptr(g_rgb), L.ptr(g_depth), L.ptr(d_raw), R, S, st)
         if g_raw is not None:
@@ -326,10 +343,11 @@ class JointEncoding(nn.Module):
         dev = self._device
         rays_o, rays_d = L.f32c(rays_o, dev), L.f32c(rays_d, dev)
         R = rays_o.shape[0]
+        # targets may stay row-strided views (the loop's column slices of its (R,10) batch tensor): the kernels take a row stride
         if target_d is not None:
-            target_d = L.f32c(target_d, dev).reshape(R)
+            target_d = target_d if _row_view(target_d, dev, R, 1) else L.f32c(target_d, dev).reshape(R)
         if target_rgb is not None:
-            target_rgb = L.f32c(target_rgb, dev)
+            target_rgb = target_rgb if _row_view(target_rgb, dev, R, 3) else L.f32c(target_rgb, dev)
         tr = self.config["training"]
         S = (tr["n_samples_d"] + tr["n_range_d"]) if target_d is not None else tr["n_samples"]
         if tr["perturb"] > 0.0:

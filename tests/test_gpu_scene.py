@@ -336,3 +336,34 @@ def test_one_launch_optimizer_step_equals_per_tensor_path_and_flat_storage_seman
     m_ref = H.cuda_model(cfg, H.state_of(of))
     with torch.no_grad():
         assert torch.equal(m_fast.run_network(pts), m_ref.run_network(pts))
+
+
+@pytest.mark.gpu
+def test_forward_on_batch_slices_equals_forward_on_contiguous_copies():
+    """The reference's loop slices one (R,10) device tensor into rays_o / rays_d / target_rgb / target_d (mipsfusion.py:316-322);
+    the targets are then read in place through their row stride (mf_sample_z_ld, mf_render_loss_fwd_ld,
+    mf_render_loss_bwd_scalars) -- nothing may change."""
+    cfg = H.make_config(12, n_samples_d=32, n_range_d=11)
+    of = H.oracle_field(cfg, grid_scale=0.3)
+    R, S = 333, 43
+    rays_o, rays_d, rgb, d, u = H.synth_batch(R, S, seed=5)
+    batch = torch.cat([rays_o, rays_d, rgb, d.reshape(R, 1)], -1).cuda()
+    outs = []
+    for sliced in (True, False):
+        model = H.cuda_model(cfg, H.state_of(of))
+        a = [batch[:, 0:3], batch[:, 3:6], batch[:, 6:9], batch[:, 9:10]]
+        if not sliced:
+            a = [t.contiguous() for t in a]
+        ret = model(*a, u=u.cuda())
+        loss = ret["rgb_loss"] + 1000.0 * ret["sdf_loss"] + 10.0 * ret["fs_loss"]
+        loss.backward()
+        outs.append((float(loss), ret["rgb"].detach().clone(), ret["depth"].detach().clone(), model.embed_fn.params.grad.detach().clone()))
+    assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    # (grid gradients are float atomics: equal up to summation order)
+    assert H.rel_err(outs[0][3].cpu().numpy(), outs[1][3].cpu().numpy()) < 1e-5
+    # evaluation route with a strided depth view
+    model.eval()
+    with torch.no_grad():
+        r1 = model.render_rays(batch[:, 0:3], batch[:, 3:6], batch[:, 9:10], u=u.cuda())
+        r2 = model.render_rays(batch[:, 0:3].contiguous(), batch[:, 3:6].contiguous(), batch[:, 9:10].contiguous(), u=u.cuda())
+    assert torch.equal(r1["rgb"], r2["rgb"]) and torch.equal(r1["depth"], r2["depth"])
